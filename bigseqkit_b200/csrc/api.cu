@@ -1,0 +1,164 @@
+// api.cu -- extern "C" boundary of libbsk.so (declarations: include/bsk.h).
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "bsk.h"
+#include "engine.h"
+
+struct bsk_ctx {
+  bsk::Engine *eng;
+};
+
+static thread_local std::string g_create_err;
+
+#define BSK_GUARD(ctx, body)                                      \
+  try {                                                           \
+    body                                                          \
+  } catch (const bsk::CudaError &e) {                             \
+    (ctx)->eng->err = e.what();                                   \
+    return BSK_ERR_CUDA;                                          \
+  } catch (const std::bad_alloc &) {                              \
+    (ctx)->eng->err = "out of host memory";                       \
+    return BSK_ERR_CUDA;                                          \
+  } catch (const std::exception &e) {                             \
+    (ctx)->eng->err = e.what();                                   \
+    return BSK_ERR_CUDA;                                          \
+  }
+
+extern "C" {
+
+int bsk_version(void) { return 100; }
+
+int bsk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *bsk_create_error(void) { return g_create_err.c_str(); }
+
+int bsk_create(const char *op, const char *opts_json, int device, bsk_ctx **out) {
+  if (!out) return BSK_ERR_ARG;
+  *out = nullptr;
+  g_create_err.clear();
+  const bsk::Op o = bsk::op_from_name(op);
+  if (o == bsk::OP_INVALID) {
+    g_create_err = std::string("unknown operator: ") + (op ? op : "(null)");
+    return BSK_ERR_ARG;
+  }
+  bsk::Opts opts;
+  int code = BSK_OK;
+  if (!bsk::parse_and_validate(o, opts_json, opts, g_create_err, code)) return code;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    g_create_err = "no CUDA device available: libbsk has no CPU fallback";
+    return BSK_ERR_CUDA;
+  }
+  if (device >= ndev) {
+    g_create_err = "device index out of range";
+    return BSK_ERR_ARG;
+  }
+  try {
+    bsk_ctx *c = new bsk_ctx;
+    c->eng = new bsk::Engine(o, opts, device);
+    *out = c;
+  } catch (const std::exception &e) {
+    g_create_err = e.what();
+    return BSK_ERR_CUDA;
+  }
+  return BSK_OK;
+}
+
+void bsk_destroy(bsk_ctx *ctx) {
+  if (!ctx) return;
+  delete ctx->eng;
+  delete ctx;
+}
+
+const char *bsk_last_error(const bsk_ctx *ctx) { return ctx ? ctx->eng->err.c_str() : "null ctx"; }
+
+int bsk_set_elem_offsets(bsk_ctx *ctx, int want) {
+  if (!ctx) return BSK_ERR_ARG;
+  ctx->eng->want_elem_off = want ? 1 : 0;
+  return BSK_OK;
+}
+
+int bsk_reset(bsk_ctx *ctx) {
+  if (!ctx) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->reset();)
+}
+
+int bsk_run_buffer(bsk_ctx *ctx, const uint8_t *in, size_t n, int64_t partition_id, bsk_out *out) {
+  if (!ctx || !out || (!in && n)) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->run_buffer(in, n, partition_id, out);)
+}
+
+int bsk_run_device(bsk_ctx *ctx, const void *d_in, size_t n, int64_t partition_id, bsk_out *out) {
+  if (!ctx || !out || (!d_in && n)) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->run_device(d_in, n, partition_id, out);)
+}
+
+void *bsk_stream(bsk_ctx *ctx) { return ctx ? (void *)ctx->eng->stream : nullptr; }
+
+int bsk_get_timings(const bsk_ctx *ctx, bsk_timings *t) {
+  if (!ctx || !t) return BSK_ERR_ARG;
+  *t = ctx->eng->timings;
+  return BSK_OK;
+}
+
+int bsk_stats_result(bsk_ctx *ctx, bsk_stats *out) {
+  if (!ctx || !out) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->stats_result(out);)
+}
+
+int bsk_stats_merge(bsk_ctx *dst, const bsk_ctx *src) {
+  if (!dst || !src) return BSK_ERR_ARG;
+  BSK_GUARD(dst, return dst->eng->stats_merge_from(*src->eng);)
+}
+
+int bsk_stats_add(bsk_ctx *ctx, const uint64_t *hist_len, const uint64_t *hist_cnt, size_t n_hist, uint64_t q20,
+                  uint64_t q30, uint64_t sum_gap, const char *type) {
+  if (!ctx) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->stats_add(hist_len, hist_cnt, n_hist, q20, q30, sum_gap, type);)
+}
+
+int bsk_stats_dense_device(bsk_ctx *ctx, void *d_hist_u64, size_t nbins, uint64_t *n_overflow) {
+  if (!ctx || !d_hist_u64) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->stats_dense_device(d_hist_u64, nbins, n_overflow);)
+}
+
+long bsk_stats_render(bsk_ctx *ctx, const char *file, const char *format, char *buf, size_t cap) {
+  if (!ctx) return -1;
+  try {
+    return ctx->eng->stats_render(file ? file : "", format ? format : "", buf, cap);
+  } catch (const std::exception &e) {
+    ctx->eng->err = e.what();
+    return -1;
+  }
+}
+
+int bsk_rmdup_keys(bsk_ctx *ctx, const int64_t **keys, size_t *n) {
+  if (!ctx || !keys || !n) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->rmdup_keys(keys, n);)
+}
+
+uint64_t bsk_rmdup_removed(const bsk_ctx *ctx) { return ctx ? ctx->eng->rmdup_removed : 0; }
+
+int bsk_rmdup_prepare_device(bsk_ctx *ctx, const void *d_in, size_t n, void *d_fp, size_t fp_cap, uint64_t *n_records) {
+  if (!ctx) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->rmdup_prepare_device(d_in, n, d_fp, fp_cap, n_records);)
+}
+
+int bsk_rmdup_resolve_device(bsk_ctx *ctx, const void *d_all_fp, uint64_t n_before, bsk_out *out) {
+  if (!ctx || !out) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->rmdup_resolve_device(d_all_fp, n_before, out);)
+}
+
+uint64_t bsk_grep_count(const bsk_ctx *ctx) { return ctx ? ctx->eng->grep_count : 0; }
+
+}  // extern "C"

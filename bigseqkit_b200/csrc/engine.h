@@ -1,0 +1,133 @@
+// engine.h -- host-side operator objects behind the C ABI (include/bsk.h).
+//
+// One Engine == one reference operator instance between Before() and After()
+// (bigseqkit-lib/seq.go:21-26 SeqTransform, stats.go Stats, rmdup.go RmDupPrepare/
+// RmDupCheck, translate.go Translate, locate.go Locate, grep.go Grep, subseq.go
+// SubseqTransform), bound to one CUDA device and one stream.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bsk.h"
+#include "devbuf.h"
+#include "kernels.h"
+#include "opts.h"
+
+namespace bsk {
+
+static const size_t kMaxBlockBytes = 0xFFF00000ull;  // offsets inside a block are u32
+
+struct BlockOut {
+  u8 *d_data = nullptr;
+  u64 n = 0;
+  u64 *d_elem_off = nullptr;  // n_elem + 1 entries (device) when wanted
+  u64 n_elem = 0;
+  u64 n_rec = 0;
+};
+
+class Engine {
+ public:
+  Engine(Op op, const Opts &o, int device);
+  ~Engine();
+
+  int run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out);
+  int run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out);
+  int reset();
+
+  // stats
+  int stats_result(bsk_stats *out);
+  int stats_add(const u64 *len, const u64 *cnt, size_t n, u64 q20, u64 q30, u64 gap, const char *type);
+  int stats_merge_from(const Engine &src);
+  int stats_dense_device(void *d_hist, size_t nbins, u64 *n_overflow);
+  long stats_render(const char *file, const char *format, char *buf, size_t cap);
+
+  // rmdup
+  int rmdup_keys(const int64_t **keys, size_t *n);
+  int rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records);
+  int rmdup_resolve_device(const void *d_all_fp, u64 n_before, bsk_out *out);
+
+  std::string err;
+  int want_elem_off = 1;
+  bsk_timings timings{};
+  cudaStream_t stream = nullptr;
+  u64 rmdup_removed = 0;
+  u64 grep_count = 0;
+
+ private:
+  Op op_;
+  Opts o_;
+  int device_;
+
+  // ---- per-partition state (alphabet is guessed on the first record of a partition)
+  int alphabet_ = AB_NIL;  // resolved alphabet of the running partition
+  bool alphabet_known_ = false;
+  int first_guess_ = AB_UNLIMIT;  // plain guess on the first record (stats "type" fallback)
+  bool first_block_ = true;
+  bool part_fastq_ = false;
+  bool any_record_ = false;
+
+  // ---- per-block device state
+  const u8 *in_ = nullptr;
+  u32 n_ = 0;
+  u32 n_nl_ = 0, n_rec_ = 0, n_lines_ = 0;
+  bool fastq_ = false;
+  bool squeezed_ = false;
+  RecIndex ix_{};
+  RecArrays ra_{};
+  RecViews views_{};
+  u32 seq_space_ = 0, qual_space_ = 0;  // size of the byte space seq_off / qual_off index into
+
+  DevStatus *d_status_ = nullptr;
+  DevStatus *h_status_ = nullptr;  // pinned
+  DevBuf b_in_, b_tile_, b_tile_scan_, b_ls_, b_rl_, b_rec_, b_seq_aoff_, b_qual_aoff_, b_seq_arena_, b_qual_arena_;
+  DevBuf b_tmp_, b_keep_, b_out_len_, b_out_off_, b_out_, b_elem_, b_id_, b_gap_seq_, b_gap_qual_, b_newlen_;
+  DevBuf b_tables_, b_lens_sorted_, b_rle_u_, b_rle_c_;
+  DevBuf b_op1_, b_op2_, b_op3_, b_op4_, b_op5_, b_op6_, b_op7_, b_op8_;
+  PinnedBuf h_out_, h_elem_, h_small_;
+  u64 launches_ = 0;
+
+  // device constant tables (one allocation): class masks, valid[], lut, gap, qual_pow, ...
+  u8 *t_class_ = nullptr, *t_valid_ = nullptr, *t_lut_ = nullptr, *t_gap_ = nullptr, *t_aux_ = nullptr;
+  double *t_qpow_ = nullptr;
+
+  // ---- stats accumulation (host)
+  std::map<u64, u64> hist_;
+  u64 q20_ = 0, q30_ = 0, gap_ = 0;
+  std::string stats_type_;
+  bool stats_type_set_ = false;
+  std::vector<u64> hist_len_v_, hist_cnt_v_;
+
+  // ---- rmdup state
+  std::vector<int64_t> keys_host_;
+  struct RmdupState;
+  RmdupState *rm_ = nullptr;
+
+  // ---- locate / grep / translate host-prepared tables
+  struct PatternSet;
+  PatternSet *pats_ = nullptr;
+
+  void free_op_state();
+  void reset_op_state();
+  void reset_status();
+  void fetch_status();
+  int prepare_block(const u8 *d_in, u32 n);
+  int resolve_alphabet();
+  int check_errors();
+  std::string describe_error(u64 rec, u32 kind);
+  void upload_tables();
+  void set_views_default();
+
+  int process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo);
+  int op_seq(BlockOut &bo);
+  int op_stats(BlockOut &bo);
+  int op_rmdup(BlockOut &bo, bool prepare_only);
+  int op_translate(BlockOut &bo);
+  int op_locate(BlockOut &bo, int64_t pid);
+  int op_grep(BlockOut &bo);
+  int op_subseq(BlockOut &bo);
+  int emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, BlockOut &bo);
+  void finalize_stats(bsk_stats *s);
+};
+
+}  // namespace bsk

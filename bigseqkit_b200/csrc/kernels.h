@@ -1,0 +1,97 @@
+// kernels.h -- device data layout and host-side launchers of the CUDA kernels.
+//
+// HBM layout of one partition block (n < 4 GiB, so every offset is a u32):
+//   in[n]            raw FASTA/FASTQ bytes as read from the file
+//   ls[n_nl + 2]     line starts: ls[0] = 0, ls[k+1] = (k-th '\n') + 1, ls[n_nl+1] = n + 1
+//                    -> line k holds bytes [ls[k], ls[k+1] - 1)
+//   rl[n_rec + 1]    first line of every record, rl[n_rec] = number of real lines
+//   per record (SoA, u32): head_off/len, seq_off/len (+ line run), qual_off/len (+ line run)
+//   seq / qual arenas  only when some record spreads its sequence over several lines
+//   out_len[n_rec+1] -> out_off[n_rec+1] (u64, exclusive scan) -> out[total]
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "cuda_compat.h"
+
+namespace bsk {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// error kinds, ordered by the position of the check inside SeqParser.Read / Call
+enum ErrKind : u32 { EK_VALIDATE = 0, EK_UNMATCHED = 1, EK_TOO_SHORT = 2, EK_UNKNOWN_CODON = 3 };
+static const u64 kNoErr = ~0ull;
+
+// device-resident status words of one call (mirrored to pinned host memory)
+struct DevStatus {
+  u64 err;         // min over (record << 8 | kind << 4 ...) ; kNoErr = none
+  u64 aux;         // error detail (e.g. offending byte, lengths)
+  u32 multiline;   // some record's sequence/quality spans several non-empty lines
+  u32 guess_mask;  // AND of alphabet class masks over the guessed prefix of record 0
+  u32 guess_len;   // number of bytes looked at
+  u32 n_sel;       // scratch counter (selected items)
+  u64 counters[8]; // op-specific totals (q20, q30, gaps, grep count, ...)
+};
+
+struct RecIndex {
+  const u8 *in;
+  u32 n;
+  const u32 *ls;
+  const u32 *rl;
+  u32 n_lines;  // real lines (rl[n_rec])
+  u32 n_rec;
+  int fastq;
+};
+
+// per-record arrays produced by the parse kernel
+struct RecArrays {
+  u32 *head_off, *head_len;
+  u32 *seq_line0, *seq_line1, *seq_off, *seq_len;      // line run [line0, line1) + contiguous offset
+  u32 *qual_line0, *qual_line1, *qual_off, *qual_len;
+};
+
+// contiguous views consumed by the operator kernels
+struct RecViews {
+  const u8 *in, *seqb, *qualb;
+  const u32 *name_off, *name_len;  // into in   (head, or ID when --only-id)
+  const u32 *seq_off, *seq_len;    // into seqb
+  const u32 *qual_off, *qual_len;  // into qualb
+  u32 n_rec;
+};
+
+struct EmitCfg {
+  u8 marker;  // '>' / '@' / 0
+  u8 print_name, print_seq, print_qual, plus_line, reverse;
+  u32 width;  // wrap width of the sequence lines (0 = single line)
+};
+
+namespace k {
+// ---- record index (k_index.cu)
+static const u32 kIndexTile = 16384;
+void index_count(const u8 *in, u32 n, u64 *tile_cnt, u32 n_tiles, cudaStream_t s);
+void index_fill(const u8 *in, u32 n, const u64 *tile_base, u32 *ls, u32 *rl, u32 n_tiles, cudaStream_t s);
+void index_finish(u32 *ls, u32 *rl, u32 n, u32 n_nl, u32 n_rec, u32 n_lines, cudaStream_t s);
+void parse_records(RecIndex ix, RecArrays ra, DevStatus *st, cudaStream_t s);
+void squeeze_lines(RecIndex ix, RecArrays ra, const u32 *seq_aoff, const u32 *qual_aoff, u8 *seq_arena, u8 *qual_arena,
+                   cudaStream_t s);
+void guess_alphabet(RecViews v, const u8 *class_mask, u32 limit, DevStatus *st, cudaStream_t s);
+void id_desc(RecViews v, int id_ncbi, u32 *id_off, u32 *id_len, u32 *desc_off, u32 *desc_len, cudaStream_t s);
+void validate_seq(RecViews v, const u8 *valid, u32 limit, DevStatus *st, cudaStream_t s);
+
+// ---- generic record emitter (k_emit.cu)
+void out_len(RecViews v, EmitCfg c, const u8 *keep, u32 *out_len, cudaStream_t s);
+void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, cudaStream_t s);
+
+// ---- seq (k_seq.cu)
+void remove_gaps(RecViews v, const u8 *gap, u8 *seq_out, u8 *qual_out, u32 *new_len, int has_qual, cudaStream_t s);
+void seq_filter(RecViews v, int min_len, int max_len, double min_qual, double max_qual, const double *qual_pow,
+                u8 *keep, cudaStream_t s);
+
+// ---- stats (k_stats.cu)
+void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
+
+}  // namespace k
+}  // namespace bsk
