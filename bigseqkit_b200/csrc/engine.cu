@@ -15,6 +15,7 @@ Engine::Engine(Op op, const Opts &o, int device) : op_(op), o_(o), device_(devic
   BSK_CUDA(cudaMalloc((void **)&d_status_, sizeof(DevStatus)));
   BSK_CUDA(cudaHostAlloc((void **)&h_status_, sizeof(DevStatus), cudaHostAllocDefault));
   h_small_.reserve(16384);
+  for (auto &e : ev_) BSK_CUDA(cudaEventCreate(&e));
   // constant tables: class[256] valid[256] lut[256] gap[256] aux[256] qpow[256 doubles]
   b_tables_.reserve(256 * 5 + 256 * sizeof(double) + 64);
   u8 *base = b_tables_.as<u8>();
@@ -33,6 +34,7 @@ Engine::~Engine() {
   if (stream) cudaStreamSynchronize(stream);
   if (d_status_) cudaFree(d_status_);
   if (h_status_) cudaFreeHost(h_status_);
+  for (auto &e : ev_) if (e) cudaEventDestroy(e);
   free_op_state();
   if (stream) cudaStreamDestroy(stream);
 }
@@ -268,7 +270,9 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
   u32 nsel = n_rec_;
   if (keep) memcpy(&nsel, hs + 8, 4);
   u8 *out = b_out_.get<u8>((size_t)total + 64);
+  main_begin();
   k::emit(views_, cfg, ooff, out, total, lut, stream);
+  main_end();
   launches_++;
   bo.d_data = out;
   bo.n = total;
@@ -286,14 +290,37 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
 }
 
 // ------------------------------------------------------------------ block dispatch
+void Engine::main_begin() {
+  BSK_CUDA(cudaEventRecord(ev_[2], stream));
+}
+void Engine::main_end() {
+  BSK_CUDA(cudaEventRecord(ev_[3], stream));
+  main_timed_ = true;
+  timings.main_launches++;
+}
+// call after the stream has been synchronised
+void Engine::accumulate_timings() {
+  float a = 0, b = 0, c = 0;
+  cudaEventElapsedTime(&a, ev_[0], ev_[1]);
+  cudaEventElapsedTime(&b, ev_[1], ev_[4]);
+  if (main_timed_) cudaEventElapsedTime(&c, ev_[2], ev_[3]);
+  timings.index_ms += a;
+  timings.op_ms += b;
+  timings.main_ms += c;
+  timings.total_ms += a + b;
+}
+
 int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
   bo = BlockOut();
+  main_timed_ = false;
+  BSK_CUDA(cudaEventRecord(ev_[0], stream));
   int rc = prepare_block(d_in, n);
   if (rc != BSK_OK) return rc;
   bo.n_rec = n_rec_;
   if (n_rec_) any_record_ = true;
   rc = resolve_alphabet();
   if (rc != BSK_OK) return rc;
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
   switch (op_) {
     case OP_SEQ: rc = op_seq(bo); break;
     case OP_STATS: rc = op_stats(bo); break;
@@ -306,6 +333,11 @@ int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
     default: err = "unknown operator"; rc = BSK_ERR_ARG;
   }
   first_block_ = false;
+  if (rc == BSK_OK) {
+    BSK_CUDA(cudaEventRecord(ev_[4], stream));
+    BSK_CUDA(cudaStreamSynchronize(stream));
+    accumulate_timings();
+  }
   return rc;
 }
 
@@ -315,6 +347,7 @@ int Engine::run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out) {
   if (((uintptr_t)d_in & 15) != 0) { err = "bsk_run_device: device pointer must be 16-byte aligned"; return BSK_ERR_ARG; }
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
   launches_ = 0;
+  timings = bsk_timings{};
   // a device call is one whole partition
   alphabet_ = o_.alphabet;
   alphabet_known_ = false;

@@ -86,6 +86,11 @@ class Engine {
   DevBuf b_op1_, b_op2_, b_op3_, b_op4_, b_op5_, b_op6_, b_op7_, b_op8_;
   PinnedBuf h_out_, h_elem_, h_small_;
   u64 launches_ = 0;
+  cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, indexed, main0, main1, end
+  bool main_timed_ = false;
+  void main_begin();
+  void main_end();
+  void accumulate_timings();
 
   // device constant tables (one allocation): class masks, valid[], lut, gap, qual_pow, ...
   u8 *t_class_ = nullptr, *t_valid_ = nullptr, *t_lut_ = nullptr, *t_gap_ = nullptr, *t_aux_ = nullptr;

@@ -456,6 +456,7 @@ int Engine::run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out) {
   memset(out, 0, sizeof *out);
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
   launches_ = 0;
+  timings = bsk_timings{};
   alphabet_ = o_.alphabet;
   alphabet_known_ = false;
   first_block_ = true;

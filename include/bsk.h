@@ -78,7 +78,11 @@ typedef struct {
 
 /* Per-call device timings (CUDA events on the ctx stream), for bench/profiling. */
 typedef struct {
-  float h2d_ms, index_ms, op_ms, d2h_ms, total_ms;
+  float index_ms;           /* delimiter scan -> record index -> parse (+ squeeze, alphabet guess) */
+  float op_ms;              /* operator kernels after the index, scans included */
+  float main_ms;            /* the operator's dominant kernel alone (record emitter / hash / matcher) */
+  float total_ms;           /* whole call on the ctx stream; host<->device copies included for bsk_run_buffer */
+  uint64_t main_launches;   /* launches of the dominant kernel summed in main_ms */
   uint64_t kernel_launches; /* launches of libbsk's own kernels in the last call */
   uint64_t in_bytes, out_bytes;
 } bsk_timings;
