@@ -47,6 +47,9 @@ class Engine {
   int rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records);
   int rmdup_resolve_device(const void *d_all_fp, u64 n_before, bsk_out *out);
 
+  struct RmdupState;   // ops_rmdup.cu: key table + fingerprint history of the running partition
+  struct PatternSet;   // ops_match.cu: needles of locate / grep on the device
+
   std::string err;
   int want_elem_off = 1;
   bsk_timings timings{};
@@ -103,14 +106,11 @@ class Engine {
   bool stats_type_set_ = false;
   std::vector<u64> hist_len_v_, hist_cnt_v_;
 
-  // ---- rmdup state
   std::vector<int64_t> keys_host_;
-  struct RmdupState;
   RmdupState *rm_ = nullptr;
-
-  // ---- locate / grep / translate host-prepared tables
-  struct PatternSet;
   PatternSet *pats_ = nullptr;
+  int rmdup_hash_block();
+  int rmdup_resolve_block(BlockOut &bo);
 
   void free_op_state();
   void reset_op_state();

@@ -1,0 +1,374 @@
+// ops_rmdup.cu -- rmdup: subject hashing, first-occurrence resolution, survivor emission.
+//
+//   RmDupPrepare.Call   bigseqkit-lib/rmdup.go:43-90    key = int64(xxhash.Sum64(subject))
+//   GroupByKey          bigseqkit/rmdup.go:97           -> one device hash table  key -> earliest record
+//   RmDupCheck.Call     bigseqkit-lib/rmdup.go:118-242  exact-subject compare inside an equal-key group, first wins
+// Pinned semantics: the first occurrence in input order survives, output in input order.
+#include <cstring>
+
+#include "engine.h"
+#include "op_state.h"
+#include "prims.h"
+#include "xxh64.cuh"
+
+namespace bsk {
+
+static const u64 kSeedB = 0x9E3779B97F4A7C15ull;
+static const u64 kNoFirst = ~0ull;
+
+struct SubjectViews {
+  const u8 *base;
+  const u32 *off, *len;
+};
+
+struct GetRaw {
+  const u8 *p;
+  __host__ __device__ __forceinline__ u8 operator()(u32 i) const { return p[i]; }
+};
+struct GetLower {
+  const u8 *p;
+  __host__ __device__ __forceinline__ u8 operator()(u32 i) const {
+    const u8 c = p[i];
+    return (c >= 'A' && c <= 'Z') ? (u8)(c + 32) : c;  // bytes.ToLower on ASCII
+  }
+};
+
+// one thread per record
+__global__ void k_rmdup_hash(SubjectViews sv, u32 n_rec, int ignore_case, u64 *__restrict__ keys, u64 *__restrict__ fps) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rec) return;
+  const u8 *p = sv.base + sv.off[r];
+  const u32 len = sv.len[r];
+  u64 a, b;
+  if (ignore_case) xxh64_pair(GetLower{p}, len, 0, kSeedB, a, b, true);
+  else xxh64_pair(GetRaw{p}, len, 0, kSeedB, a, b, true);
+  keys[r] = a;
+  fps[r] = b;
+}
+
+// open addressing, linear probing; key 0 lives in the extra slot `cap`
+__device__ __forceinline__ u64 table_slot(u64 *tkeys, u64 cap, u64 key, bool insert) {
+  if (key == 0) return cap;
+  u64 i = (key * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
+  for (;;) {
+    u64 cur = tkeys[i];
+    if (cur == key) return i;
+    if (cur == 0) {
+      if (!insert) return ~0ull;
+      const u64 old = atomicCAS((unsigned long long *)&tkeys[i], 0ull, (unsigned long long)key);
+      if (old == 0 || old == key) return i;
+    }
+    i = (i + 1) & (cap - 1);
+  }
+}
+
+__global__ void k_table_insert(const u64 *__restrict__ keys, u64 n, u64 g_base, u64 *tkeys, u64 *tfirst, u64 cap) {
+  const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const u64 s = table_slot(tkeys, cap, keys[r], true);
+  atomicMin((unsigned long long *)&tfirst[s], (unsigned long long)(g_base + r));
+}
+
+__device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32 b, int ignore_case) {
+  const u32 la = sv.len[a];
+  if (la != sv.len[b]) return false;
+  const u8 *pa = sv.base + sv.off[a], *pb = sv.base + sv.off[b];
+  if (ignore_case) {
+    GetLower ga{pa}, gb{pb};
+    for (u32 i = 0; i < la; i++)
+      if (ga(i) != gb(i)) return false;
+  } else {
+    for (u32 i = 0; i < la; i++)
+      if (pa[i] != pb[i]) return false;
+  }
+  return true;
+}
+
+// keep[r]: 1 first occurrence, 0 duplicate, 2 unresolved (64-bit key collision between different subjects)
+__global__ void k_rmdup_resolve(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *__restrict__ keys,
+                                const u64 *__restrict__ fps, u64 g_base, const u64 *__restrict__ hist_fp, u64 *tkeys,
+                                const u64 *__restrict__ tfirst, u64 cap, u8 *__restrict__ keep, DevStatus *st) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rec) return;
+  const u64 g = g_base + r;
+  const u64 s = table_slot(tkeys, cap, keys[r], false);
+  const u64 first = tfirst[s];
+  u8 k;
+  if (first == g) k = 1;
+  else if (first >= g_base) k = subject_equal(sv, r, (u32)(first - g_base), ignore_case) ? 0 : 2;
+  else k = (hist_fp[first] == fps[r]) ? 0 : 2;  // earlier block / other GPU: second 64-bit hash decides
+  keep[r] = k;
+  if (k == 2) atomicAdd((unsigned long long *)&st->counters[4], 1ull);
+}
+
+// rare path: serial scan for the records whose key collided with a different subject
+__global__ void k_rmdup_fixup(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *keys, const u64 *fps, u64 g_base,
+                              const u64 *hist_keys, const u64 *hist_fp, u8 *keep) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (u32 r = 0; r < n_rec; r++) {
+    if (keep[r] != 2) continue;
+    bool dup = false;
+    for (u64 h = 0; h < g_base && !dup; h++) dup = hist_keys[h] == keys[r] && hist_fp[h] == fps[r];
+    for (u32 q = 0; q < r && !dup; q++) dup = keys[q] == keys[r] && subject_equal(sv, r, q, ignore_case);
+    keep[r] = dup ? 0 : 1;
+  }
+}
+
+__global__ void k_interleave_fp(const u64 *keys, const u64 *fps, u64 n, u64 *out) {
+  const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  out[2 * r] = keys[r];
+  out[2 * r + 1] = fps[r];
+}
+__global__ void k_deinterleave_fp(const u64 *in, u64 n, u64 *keys, u64 *fps) {
+  const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  keys[r] = in[2 * r];
+  fps[r] = in[2 * r + 1];
+}
+
+// ------------------------------------------------------------------ host side
+static void hist_reserve(Engine::RmdupState *rm, u64 need, cudaStream_t s) {
+  if (need <= rm->hist_cap) return;
+  u64 cap = rm->hist_cap ? rm->hist_cap : (1u << 16);
+  while (cap < need) cap *= 2;
+  u64 *nk = nullptr, *nf = nullptr;
+  BSK_CUDA(cudaMalloc((void **)&nk, cap * 8));
+  BSK_CUDA(cudaMalloc((void **)&nf, cap * 8));
+  if (rm->n_hist) {
+    BSK_CUDA(cudaMemcpyAsync(nk, rm->hist_keys, rm->n_hist * 8, cudaMemcpyDeviceToDevice, s));
+    BSK_CUDA(cudaMemcpyAsync(nf, rm->hist_fp, rm->n_hist * 8, cudaMemcpyDeviceToDevice, s));
+    BSK_CUDA(cudaStreamSynchronize(s));
+  }
+  if (rm->hist_keys) cudaFree(rm->hist_keys);
+  if (rm->hist_fp) cudaFree(rm->hist_fp);
+  rm->hist_keys = nk;
+  rm->hist_fp = nf;
+  rm->hist_cap = cap;
+}
+
+static void table_reserve(Engine::RmdupState *rm, u64 total, cudaStream_t s, u64 &launches) {
+  if (rm->cap && total * 2 <= rm->cap) return;
+  u64 cap = 1u << 12;
+  while (cap < total * 4) cap *= 2;
+  if (rm->tkeys) cudaFree(rm->tkeys);
+  if (rm->tfirst) cudaFree(rm->tfirst);
+  BSK_CUDA(cudaMalloc((void **)&rm->tkeys, (cap + 1) * 8));
+  BSK_CUDA(cudaMalloc((void **)&rm->tfirst, (cap + 1) * 8));
+  BSK_CUDA(cudaMemsetAsync(rm->tkeys, 0, (cap + 1) * 8, s));
+  BSK_CUDA(cudaMemsetAsync(rm->tfirst, 0xff, (cap + 1) * 8, s));
+  rm->cap = cap;
+  if (rm->n_hist) {
+    BSK_LAUNCH_FLAT(k_table_insert, (u32)((rm->n_hist + 255) / 256), 256, 0, s, rm->hist_keys, rm->n_hist, (u64)0, rm->tkeys,
+                    rm->tfirst, cap);
+    launches++;
+  }
+}
+
+void rmdup_state_free(Engine::RmdupState *rm) {
+  if (!rm) return;
+  if (rm->tkeys) cudaFree(rm->tkeys);
+  if (rm->tfirst) cudaFree(rm->tfirst);
+  if (rm->hist_keys) cudaFree(rm->hist_keys);
+  if (rm->hist_fp) cudaFree(rm->hist_fp);
+  delete rm;
+}
+
+void rmdup_state_reset(Engine::RmdupState *rm) {
+  if (!rm) return;
+  rm->n_hist = 0;
+  if (rm->tkeys) cudaFree(rm->tkeys);
+  if (rm->tfirst) cudaFree(rm->tfirst);
+  rm->tkeys = rm->tfirst = nullptr;
+  rm->cap = 0;
+  rm->block_ready = false;
+}
+
+int Engine::rmdup_hash_block() {
+  if (!rm_) rm_ = new RmdupState();
+  const size_t R = (size_t)n_rec_ + 1;
+  SubjectViews sv;
+  if (o_.BySeq) {
+    sv = SubjectViews{views_.seqb, views_.seq_off, views_.seq_len};
+  } else if (o_.ByName) {
+    sv = SubjectViews{in_, ra_.head_off, ra_.head_len};
+  } else {
+    u32 *ids = b_id_.get<u32>(R * 2);
+    k::id_desc(views_, o_.IDNCBI ? 1 : 0, ids, ids + R, nullptr, nullptr, stream);
+    launches_++;
+    sv = SubjectViews{in_, ids, ids + R};
+  }
+  rm_->sv_base = sv.base;
+  rm_->sv_off = sv.off;
+  rm_->sv_len = sv.len;
+  u64 *keys = b_op1_.get<u64>(R);
+  u64 *fps = b_op2_.get<u64>(R);
+  if (n_rec_) {
+    main_begin();
+    BSK_LAUNCH_FLAT(k_rmdup_hash, (n_rec_ + 127) / 128, 128, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps);
+    main_end();
+    launches_++;
+  }
+  return BSK_OK;
+}
+
+int Engine::rmdup_resolve_block(BlockOut &bo) {
+  RmdupState *rm = rm_;
+  const u64 g_base = rm->n_hist;
+  u64 *keys = b_op1_.as<u64>(), *fps = b_op2_.as<u64>();
+  SubjectViews sv{rm->sv_base, rm->sv_off, rm->sv_len};
+  u8 *keep = b_keep_.get<u8>((size_t)n_rec_ + 1);
+  if (n_rec_) {
+    table_reserve(rm, g_base + n_rec_, stream, launches_);
+    BSK_LAUNCH_FLAT(k_table_insert, (n_rec_ + 255) / 256, 256, 0, stream, keys, (u64)n_rec_, g_base, rm->tkeys, rm->tfirst,
+                    rm->cap);
+    BSK_LAUNCH_FLAT(k_rmdup_resolve, (n_rec_ + 255) / 256, 256, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps,
+                    g_base, rm->hist_fp, rm->tkeys, rm->tfirst, rm->cap, keep, d_status_);
+    launches_ += 2;
+    fetch_status();
+    if (h_status_->counters[4]) {
+      BSK_LAUNCH_FLAT(k_rmdup_fixup, 1, 1, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps, g_base, rm->hist_keys,
+                      rm->hist_fp, keep);
+      launches_++;
+    }
+    hist_reserve(rm, g_base + n_rec_, stream);
+    BSK_CUDA(cudaMemcpyAsync(rm->hist_keys + g_base, keys, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
+    BSK_CUDA(cudaMemcpyAsync(rm->hist_fp + g_base, fps, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
+    rm->n_hist = g_base + n_rec_;
+  }
+  // Record.Format(LineWidth) minus the final '\n' (rmdup.go:214-215) + FileStore's '\n'
+  EmitCfg cfg;
+  cfg.marker = fastq_ ? '@' : '>';
+  cfg.print_name = 1;
+  cfg.print_seq = 1;
+  cfg.print_qual = fastq_;
+  cfg.plus_line = fastq_;
+  cfg.reverse = 0;
+  cfg.width = fastq_ ? 0 : (o_.LineWidth > 0 ? (u32)o_.LineWidth : 0);
+  views_.name_off = ra_.head_off;
+  views_.name_len = ra_.head_len;
+  int rc = emit_records(cfg, n_rec_ ? keep : nullptr, nullptr, bo);
+  if (rc == BSK_OK) rmdup_removed += n_rec_ - bo.n_elem;
+  return rc;
+}
+
+int Engine::op_rmdup(BlockOut &bo, bool prepare_only) {
+  int rc = check_errors();
+  if (rc != BSK_OK) return rc;
+  if (first_block_) {  // a new partition: forget the previous one
+    if (rm_) rmdup_state_reset(rm_);
+    rmdup_removed = 0;
+  }
+  rc = rmdup_hash_block();
+  if (rc != BSK_OK) return rc;
+  if (!prepare_only) return rmdup_resolve_block(bo);
+  // RmDupPrepare: every record formatted, keys kept for bsk_rmdup_keys
+  RmdupState *rm = rm_;
+  if (n_rec_) {
+    hist_reserve(rm, rm->n_hist + n_rec_, stream);
+    BSK_CUDA(cudaMemcpyAsync(rm->hist_keys + rm->n_hist, b_op1_.p, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
+    BSK_CUDA(cudaMemcpyAsync(rm->hist_fp + rm->n_hist, b_op2_.p, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
+    rm->n_hist += n_rec_;
+  }
+  EmitCfg cfg;
+  cfg.marker = fastq_ ? '@' : '>';
+  cfg.print_name = 1;
+  cfg.print_seq = 1;
+  cfg.print_qual = fastq_;
+  cfg.plus_line = fastq_;
+  cfg.reverse = 0;
+  cfg.width = fastq_ ? 0 : (o_.LineWidth > 0 ? (u32)o_.LineWidth : 0);
+  views_.name_off = ra_.head_off;
+  views_.name_len = ra_.head_len;
+  return emit_records(cfg, nullptr, nullptr, bo);
+}
+
+int Engine::rmdup_keys(const int64_t **keys, size_t *n) {
+  if (op_ != OP_RMDUP && op_ != OP_RMDUP_PREPARE) { err = "bsk_rmdup_keys: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
+  if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
+  const u64 cnt = rm_ ? rm_->n_hist : 0;
+  keys_host_.resize(cnt);
+  if (cnt) BSK_CUDA(cudaMemcpy(keys_host_.data(), rm_->hist_keys, cnt * 8, cudaMemcpyDeviceToHost));
+  *keys = keys_host_.data();
+  *n = cnt;
+  return BSK_OK;
+}
+
+// multi-GPU step 1: index + hash the local shard, export {key, second hash} per record
+int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records) {
+  if (op_ != OP_RMDUP) { err = "bsk_rmdup_prepare_device: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
+  if (n >= kMaxBlockBytes) { err = "bsk_rmdup_prepare_device: shard must be smaller than 4 GiB - 1 MiB"; return BSK_ERR_ARG; }
+  if (((uintptr_t)d_in & 15) != 0) { err = "bsk_rmdup_prepare_device: device pointer must be 16-byte aligned"; return BSK_ERR_ARG; }
+  if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
+  launches_ = 0;
+  timings = bsk_timings{};
+  alphabet_ = o_.alphabet;
+  alphabet_known_ = false;
+  first_block_ = true;
+  main_timed_ = false;
+  if (!rm_) rm_ = new RmdupState();
+  rmdup_state_reset(rm_);
+  rmdup_removed = 0;
+  BSK_CUDA(cudaEventRecord(ev_[0], stream));
+  int rc = prepare_block(static_cast<const u8 *>(d_in), (u32)n);
+  if (rc != BSK_OK) return rc;
+  rc = resolve_alphabet();
+  if (rc != BSK_OK) return rc;
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  rc = check_errors();
+  if (rc != BSK_OK) return rc;
+  if (n_records) *n_records = n_rec_;
+  if ((size_t)n_rec_ > fp_cap) { err = "bsk_rmdup_prepare_device: fingerprint buffer too small"; return BSK_ERR_ARG; }
+  rc = rmdup_hash_block();
+  if (rc != BSK_OK) return rc;
+  if (n_rec_) {
+    BSK_LAUNCH_FLAT(k_interleave_fp, (n_rec_ + 255) / 256, 256, 0, stream, b_op1_.as<u64>(), b_op2_.as<u64>(), (u64)n_rec_,
+                    static_cast<u64 *>(d_fp));
+    launches_++;
+  }
+  BSK_CUDA(cudaEventRecord(ev_[4], stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  accumulate_timings();
+  timings.kernel_launches = launches_;
+  timings.in_bytes = n;
+  rm_->block_ready = true;
+  first_block_ = false;
+  return BSK_OK;
+}
+
+// multi-GPU step 3: d_all_fp holds the fingerprints of the n_before records that precede this shard
+// in global input order (what the all-gather delivered); survivors of the local shard are emitted.
+int Engine::rmdup_resolve_device(const void *d_all_fp, u64 n_before, bsk_out *out) {
+  memset(out, 0, sizeof *out);
+  if (!rm_ || !rm_->block_ready) { err = "bsk_rmdup_resolve_device: call bsk_rmdup_prepare_device first"; return BSK_ERR_STATE; }
+  if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
+  RmdupState *rm = rm_;
+  rm->block_ready = false;
+  main_timed_ = false;
+  BSK_CUDA(cudaEventRecord(ev_[0], stream));
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  if (n_before) {
+    hist_reserve(rm, n_before, stream);
+    BSK_LAUNCH_FLAT(k_deinterleave_fp, (u32)((n_before + 255) / 256), 256, 0, stream, static_cast<const u64 *>(d_all_fp),
+                    n_before, rm->hist_keys, rm->hist_fp);
+    launches_++;
+    rm->n_hist = n_before;
+    table_reserve(rm, n_before + n_rec_, stream, launches_);
+  }
+  BlockOut bo;
+  int rc = rmdup_resolve_block(bo);
+  BSK_CUDA(cudaEventRecord(ev_[4], stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  if (rc != BSK_OK) return rc;
+  accumulate_timings();
+  timings.kernel_launches = launches_;
+  timings.out_bytes = bo.n;
+  out->data = bo.d_data;
+  out->n = bo.n;
+  out->elem_off = bo.d_elem_off;
+  out->n_elem = bo.n_elem;
+  out->n_records = n_rec_;
+  return BSK_OK;
+}
+
+}  // namespace bsk

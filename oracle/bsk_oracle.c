@@ -887,6 +887,7 @@ int orc_translate(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out
       wrap_into(&ob, prot.p, prot.n, o->LineWidth);
       sink_elem(&sink, ob.p, ob.n);
     }
+    if (rc < 0) break; /* lib/translate.go:126-131: `return nil, err` aborts the partition */
   }
   if (rc == -1) snprintf(out->err, 512, "%s", p.err);
   sink_to_out(&sink, out);

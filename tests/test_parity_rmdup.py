@@ -1,0 +1,92 @@
+"""rmdup: CUDA path vs the CPU oracle (first occurrence in input order wins)."""
+import random
+
+import pytest
+
+import oracle
+from bigseqkit_b200.api import BskError, Operator
+from cases import EDGE_INPUTS, FQ_SIMPLE, fuzz_fasta, fuzz_fastq
+from util import check_parity
+
+RMDUP_OPTS = [{}, {"BySeq": True}, {"ByName": True}, {"BySeq": True, "IgnoreCase": True}, {"IgnoreCase": True},
+              {"BySeq": True, "OnlyPositiveStrand": True}, {"BySeq": True, "Config": {"LineWidth": 7}},
+              {"Config": {"IDNCBI": True}}]
+
+
+def dup_input(seed, fastq):
+    rng = random.Random(seed)
+    base = (fuzz_fastq(rng, n_rec=30, max_len=40) if fastq else fuzz_fasta(rng, n_rec=30, max_len=40, alphabet="ACGTacgt"))
+    starts = oracle.frame(base)
+    recs = [base[starts[i]:starts[i + 1]] for i in range(len(starts) - 1)]
+    out = []
+    for _ in range(120):
+        r = rng.choice(recs)
+        if rng.random() < 0.3:  # same subject, different case
+            r = r.replace(b"A", b"a") if rng.random() < 0.5 else r
+        out.append(r if r.endswith(b"\n") else r + b"\n")
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("opts", RMDUP_OPTS, ids=lambda o: str(o)[:60])
+def test_rmdup_edge_inputs(lib, opts):
+    for name, data in EDGE_INPUTS.items():
+        check_parity(lib, "RmDup", data, opts)
+
+
+@pytest.mark.parametrize("opts", RMDUP_OPTS[:5], ids=lambda o: str(o)[:60])
+def test_rmdup_with_duplicates(lib, opts):
+    for seed in range(3):
+        for fastq in (False, True):
+            data = dup_input(seed, fastq)
+            got = check_parity(lib, "RmDup", data, opts)
+            assert got is None or len(got[1]) - 1 < 120  # something was removed (None: both sides raised the same error)
+
+
+def test_rmdup_kat(lib):
+    # a/b share ACGT, key -861719356253734761 (xxh64("ACGT") as int64)
+    data = b"@a\nACGT\n+\nIIII\n@b\nACGT\n+\nJJJJ\n@c\nAGGT\n+\nIIII\n"
+    with Operator("RmDup", {"BySeq": True}, lib=lib) as o:
+        r = o.call(data)
+        assert r.data == b"@a\nACGT\n+\nIIII\n@c\nAGGT\n+\nIIII\n"
+        assert o.rmdup_removed() == 1
+        keys = o.rmdup_keys()
+    assert keys[0] == keys[1] == -861719356253734761
+
+
+def test_rmdup_keys_match_xxh64(lib):
+    xxhash = pytest.importorskip("xxhash")
+    rng = random.Random(5)
+    data = fuzz_fasta(rng, n_rec=60, max_len=300, width=0)
+    for opts in ({"BySeq": True}, {"ByName": True}, {}, {"BySeq": True, "IgnoreCase": True}):
+        with Operator("RmDupPrepare", opts, lib=lib) as o:
+            r = o.call(data)
+            keys = o.rmdup_keys()
+        assert keys == oracle.rmdup_keys(data, opts)
+        assert r.n_records == len(keys)
+    # independent pin: python-xxhash on the sequences
+    with Operator("RmDupPrepare", {"BySeq": True}, lib=lib) as o:
+        o.call(data)
+        keys = o.rmdup_keys()
+    starts = oracle.frame(data)
+    for i, k in enumerate(keys):
+        rec = data[starts[i]:starts[i + 1]]
+        seq = b"".join(rec.split(b"\n")[1:])
+        h = xxhash.xxh64(seq, seed=0).intdigest()
+        assert k == (h - (1 << 64) if h >= 1 << 63 else h)
+
+
+def test_rmdup_bad_flags(lib):
+    check_parity(lib, "RmDup", FQ_SIMPLE, {"BySeq": True, "ByName": True})
+    check_parity(lib, "RmDup", FQ_SIMPLE, {"OnlyPositiveStrand": True})
+
+
+def test_rmdup_multi_block_partition(lib, monkeypatch):
+    # the host entry point cuts a partition into record-aligned blocks; duplicates must be
+    # recognised across blocks (history of fingerprints) and the output must not depend on the cut
+    data = dup_input(11, True) * 3
+    exp = oracle.rmdup(data, {"BySeq": True})
+    monkeypatch.setenv("BSK_BLOCK_BYTES", "4096")
+    with Operator("RmDup", {"BySeq": True}, lib=lib) as o:
+        r = o.call(data)
+        assert r.data == exp[0] and list(r.elem_off) == exp[1]
+        assert o.rmdup_removed() == exp[2]
