@@ -354,6 +354,7 @@ int Engine::run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out) {
   first_block_ = true;
   BlockOut bo;
   int rc = process_block(static_cast<const u8 *>(d_in), (u32)n, pid, bo);
+  if (rc == BSK_OK && op_ == OP_GREP && o_.Count) rc = finish_grep_count(bo);
   BSK_CUDA(cudaStreamSynchronize(stream));
   timings.kernel_launches = launches_;
   timings.in_bytes = n;

@@ -109,6 +109,10 @@ class Engine {
   std::vector<int64_t> keys_host_;
   RmdupState *rm_ = nullptr;
   PatternSet *pats_ = nullptr;
+  u64 hit_cap_ = 0;
+  int build_patterns(bool only_pos);
+  int run_matcher(int mode, u8 *flags, u64 &n_hits);
+  int finish_grep_count(BlockOut &bo);
   int rmdup_hash_block();
   int rmdup_resolve_block(BlockOut &bo);
 

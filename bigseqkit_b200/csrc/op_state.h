@@ -20,6 +20,27 @@ struct Engine::RmdupState {
   bool block_ready = false;
 };
 
+// Needles of locate / grep -s: every pattern on the '+' strand and, unless only the positive
+// strand is searched, reverse(pair(pattern)) which is matched on the forward strand instead of
+// matching the pattern on a reverse-complemented copy of the sequence (bigseqkit-lib/locate.go:669-766).
+struct Engine::PatternSet {
+  int alphabet = -1;
+  bool only_pos = false;
+  u32 n_needles = 0, n_groups = 0, max_len = 0;
+  // device arrays (one allocation each)
+  DevBuf bytes;      // needle bytes arena
+  DevBuf meta;       // u32 x 4 per needle: byte offset, length, (pattern << 1 | strand), hash  (sorted by group, hash)
+  DevBuf groups;     // u32 x 4 per length group: length, first needle, needle count, table offset (u32 units)
+  DevBuf tables;     // per group: u32 table_size followed by table_size slots (needle id + 1, 0 = empty)
+  // locate rows: pattern names / pattern text
+  DevBuf pat_bytes;  // names then patterns
+  DevBuf pat_meta;   // u32 x 4 per pattern: name offset, name len, pattern offset, pattern len
+  // grep by id / name: sorted 64-bit hashes + pattern slices
+  DevBuf name_hash;  // u64 per pattern (sorted)
+  DevBuf name_meta;  // u32 x 2 per pattern: offset, len into pat_bytes (same order as name_hash)
+  u32 n_names = 0;
+};
+
 void rmdup_state_free(Engine::RmdupState *rm);
 void rmdup_state_reset(Engine::RmdupState *rm);
 

@@ -498,6 +498,19 @@ int Engine::run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out) {
     elem_used += bo.n_elem;
     pos = end;
   }
+  if (op_ == OP_GREP && o_.Count) {
+    BlockOut bo;
+    int rc = finish_grep_count(bo);
+    if (rc != BSK_OK) return rc;
+    h_out_.reserve(bo.n + 64, false, 0);
+    BSK_CUDA(cudaMemcpy(h_out_.as<u8>(), bo.d_data, bo.n, cudaMemcpyDeviceToHost));
+    out_used = bo.n;
+    elem_used = 1;
+    if (want_elem_off) {
+      h_elem_.reserve(4 * 8, false, 0);
+      h_elem_.as<u64>()[0] = 0;
+    }
+  }
   if (want_elem_off) {
     h_elem_.reserve((elem_used + 2) * 8, true, elem_used * 8);
     h_elem_.as<u64>()[elem_used] = out_used;

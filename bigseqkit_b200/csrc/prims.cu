@@ -4,6 +4,7 @@
 
 #ifndef BSK_EMU
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #else
 #include <algorithm>
 #include <numeric>
@@ -33,7 +34,7 @@ struct ToU64 {
 };
 void excl_scan_u32_to_u64(const uint32_t *in, uint64_t *out, size_t n, DevBuf &tmp, cudaStream_t s) {
   if (!n) return;
-  cub::TransformInputIterator<uint64_t, ToU64, const uint32_t *> it(in, ToU64());
+  thrust::transform_iterator<ToU64, const uint32_t *> it(in, ToU64());
   BSK_CUB(cub::DeviceScan::ExclusiveSum(d_tmp, bytes, it, out, n, s));
 }
 void excl_scan_u32(const uint32_t *in, uint32_t *out, size_t n, DevBuf &tmp, cudaStream_t s) {
@@ -53,15 +54,10 @@ void rle_u32(const uint32_t *in, uint32_t *uniq, uint32_t *counts, uint32_t *d_r
   if (!n) { BSK_CUDA(cudaMemsetAsync(d_runs, 0, 4, s)); return; }
   BSK_CUB(cub::DeviceRunLengthEncode::Encode(d_tmp, bytes, in, uniq, counts, d_runs, n, s));
 }
-void sort_pairs_u64_u32(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, int end_bit,
-                        DevBuf &tmp, cudaStream_t s) {
+void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int begin_bit,
+                        int end_bit, DevBuf &tmp, cudaStream_t s) {
   if (!n) return;
-  BSK_CUB(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
-}
-void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int end_bit,
-                        DevBuf &tmp, cudaStream_t s) {
-  if (!n) return;
-  BSK_CUB(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  BSK_CUB(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, kin, kout, vin, vout, n, begin_bit, end_bit, s));
 }
 #else
 void excl_scan_u64(const uint64_t *in, uint64_t *out, size_t n, DevBuf &, cudaStream_t) {
@@ -98,10 +94,11 @@ void rle_u32(const uint32_t *in, uint32_t *uniq, uint32_t *counts, uint32_t *d_r
   *d_runs = r;
 }
 template <class V>
-static void sort_pairs_impl(const uint64_t *kin, uint64_t *kout, const V *vin, V *vout, size_t n, int end_bit) {
+static void sort_pairs_impl(const uint64_t *kin, uint64_t *kout, const V *vin, V *vout, size_t n, int begin_bit, int end_bit) {
   std::vector<size_t> idx(n);
   std::iota(idx.begin(), idx.end(), 0);
   uint64_t mask = end_bit >= 64 ? ~0ull : ((1ull << end_bit) - 1);
+  mask &= ~((1ull << begin_bit) - 1);
   std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return (kin[a] & mask) < (kin[b] & mask); });
   std::vector<uint64_t> k2(n);
   std::vector<V> v2(n);
@@ -109,10 +106,8 @@ static void sort_pairs_impl(const uint64_t *kin, uint64_t *kout, const V *vin, V
   std::copy(k2.begin(), k2.end(), kout);
   std::copy(v2.begin(), v2.end(), vout);
 }
-void sort_pairs_u64_u32(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, int end_bit,
-                        DevBuf &, cudaStream_t) { sort_pairs_impl(kin, kout, vin, vout, n, end_bit); }
-void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int end_bit,
-                        DevBuf &, cudaStream_t) { sort_pairs_impl(kin, kout, vin, vout, n, end_bit); }
+void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int begin_bit,
+                        int end_bit, DevBuf &, cudaStream_t) { sort_pairs_impl(kin, kout, vin, vout, n, begin_bit, end_bit); }
 #endif
 
 }  // namespace prim

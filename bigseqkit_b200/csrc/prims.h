@@ -13,9 +13,8 @@ void select_flagged_u64(const uint64_t *in, const uint8_t *flags, uint64_t *out,
                         cudaStream_t s);
 void sort_u32(const uint32_t *in, uint32_t *out, size_t n, DevBuf &tmp, cudaStream_t s);
 void rle_u32(const uint32_t *in, uint32_t *uniq, uint32_t *counts, uint32_t *d_runs, size_t n, DevBuf &tmp, cudaStream_t s);
-void sort_pairs_u64_u32(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, size_t n, int end_bit,
-                        DevBuf &tmp, cudaStream_t s);
-void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int end_bit,
-                        DevBuf &tmp, cudaStream_t s);
+// stable LSD radix sort on key bits [begin_bit, end_bit)
+void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin, uint64_t *vout, size_t n, int begin_bit,
+                        int end_bit, DevBuf &tmp, cudaStream_t s);
 }  // namespace prim
 }  // namespace bsk
