@@ -37,7 +37,7 @@ class _Stats(C.Structure):
 class _Timings(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("index_ms", "op_ms", "main_ms", "total_ms")] + \
                [("main_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("in_bytes", C.c_uint64),
-                ("out_bytes", C.c_uint64)]
+                ("out_bytes", C.c_uint64), ("fused_blocks", C.c_uint64)]
 
 
 # every symbol include/bsk.h declares (checked by tests/test_abi.py)

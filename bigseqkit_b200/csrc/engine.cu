@@ -27,6 +27,7 @@ Engine::Engine(Op op, const Opts &o, int device) : op_(op), o_(o), device_(devic
   t_qpow_ = reinterpret_cast<double *>(base + 1280);
   alphabet_ = o_.alphabet;
   alphabet_known_ = false;
+  fused_ok_ = getenv("BSK_NO_FUSED") == nullptr;  // debugging aid: force the general index/parse/emit path
 }
 
 Engine::~Engine() {
@@ -314,6 +315,20 @@ int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
   bo = BlockOut();
   main_timed_ = false;
   BSK_CUDA(cudaEventRecord(ev_[0], stream));
+  if (seq_fused_eligible()) {
+    const int frc = op_seq_fused(d_in, n, bo);
+    if (frc != kFusedFallback) {
+      first_block_ = false;
+      if (frc == BSK_OK) {
+        BSK_CUDA(cudaEventRecord(ev_[4], stream));
+        BSK_CUDA(cudaStreamSynchronize(stream));
+        accumulate_timings();
+      }
+      return frc;
+    }
+    bo = BlockOut();
+    BSK_CUDA(cudaEventRecord(ev_[0], stream));
+  }
   int rc = prepare_block(d_in, n);
   if (rc != BSK_OK) return rc;
   bo.n_rec = n_rec_;

@@ -129,6 +129,16 @@ class Engine {
 
   int process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo);
   int op_seq(BlockOut &bo);
+  // single-pass tile kernel for short records (k_fused.cu); returns kFusedFallback when the block
+  // must take the general path instead
+  static const int kFusedFallback = 1000;
+  bool fused_ok_ = true;
+  bool seq_fused_eligible() const;
+  void seq_emit_cfg(bool fastq, EmitCfg &cfg, u8 *lut, bool &need_lut) const;
+  int op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo);
+  int first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok);
+  DevBuf b_tiles_;
+  PinnedBuf h_probe_;
   int op_stats(BlockOut &bo);
   int op_rmdup(BlockOut &bo, bool prepare_only);
   int op_translate(BlockOut &bo);

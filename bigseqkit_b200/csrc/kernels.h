@@ -90,6 +90,13 @@ void remove_gaps(RecViews v, const u8 *gap, u8 *seq_out, u8 *qual_out, u32 *new_
 void seq_filter(RecViews v, int min_len, int max_len, double min_qual, double max_qual, const double *qual_pow,
                 u8 *keep, cudaStream_t s);
 
+// ---- single-pass tile kernels for short records (k_fused.cu)
+size_t fused_smem_bytes();
+size_t fused_tile_state_bytes(u32 n);
+u32 fused_max_records(u32 n);
+void seq_fused(const u8 *in, u32 n, u8 *out, u64 *elem_off, const u8 *lut, void *tile_state, u32 *ticket, DevStatus *st,
+               EmitCfg cfg, int only_id, int fastq, int min_len, int max_len, cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

@@ -1,0 +1,179 @@
+// ops_fused.cu -- host side of the single-pass tile path (k_fused.cu) for `seq` on short records.
+#include <cstring>
+
+#include "engine.h"
+#include "prims.h"
+
+namespace bsk {
+
+// print mode + byte map of SeqTransform.Call (bigseqkit-lib/seq.go:151-163, 188-239), shared by both paths
+void Engine::seq_emit_cfg(bool fastq, EmitCfg &cfg, u8 *lut, bool &need_lut) const {
+  bool print_name = true, print_seq = true, print_qual = fastq;
+  if (o_.Name && o_.Seq) {
+  } else if (o_.Name) {
+    print_seq = false;
+    print_qual = false;
+  } else if (o_.Seq) {
+    print_name = false;
+    print_qual = false;
+  } else if (o_.Qual) {
+    print_name = false;
+    print_seq = false;
+    print_qual = true;
+  }
+  cfg.marker = (print_name && print_seq) ? (fastq ? '@' : '>') : 0;
+  cfg.print_name = print_name;
+  cfg.print_seq = print_seq;
+  cfg.print_qual = print_qual;
+  cfg.plus_line = print_qual && !o_.Qual;
+  cfg.reverse = o_.Reverse;
+  int width = o_.LineWidth;
+  if (o_.Seq || o_.Qual) width = 0;  // seq.go:106-108
+  if (fastq) width = 0;              // seq.go:123
+  cfg.width = width > 0 ? (u32)width : 0;
+  // complement -> dna2rna / rna2dna -> case, one table
+  need_lut = false;
+  const u8 *pair = alphabet_pair(alphabet_ == AB_NIL ? AB_UNLIMIT : alphabet_);
+  const bool comp = o_.Complement && alphabet_ != AB_UNLIMIT && alphabet_ != AB_NIL;
+  const bool is_rna = alphabet_ == AB_RNA || alphabet_ == AB_RNARED, is_dna = alphabet_ == AB_DNA || alphabet_ == AB_DNARED;
+  for (int c = 0; c < 256; c++) {
+    u8 x = (u8)c;
+    if (comp) x = pair[x];
+    if (o_.Dna2rna && !is_rna) x = x == 't' ? 'u' : (x == 'T' ? 'U' : x);
+    if (o_.Rna2dna && !is_dna) x = x == 'u' ? 't' : (x == 'U' ? 'T' : x);
+    if (o_.LowerCase) { if (x >= 'A' && x <= 'Z') x = (u8)(x + 32); }
+    else if (o_.UpperCase) { if (x >= 'a' && x <= 'z') x = (u8)(x - 32); }
+    lut[c] = x;
+    if (x != (u8)c) need_lut = true;
+  }
+}
+
+bool Engine::seq_fused_eligible() const {
+  if (!fused_ok_ || op_ != OP_SEQ) return false;
+  if (o_.RemoveGaps || o_.MinQual > 0 || o_.MaxQual > 0) return false;
+  if (o_.ValidateSeq || !(o_.alphabet == AB_NIL || o_.alphabet == AB_UNLIMIT)) return false;  // validation needs the general path
+  if (o_.OnlyId && o_.IDNCBI) return false;
+  return true;
+}
+
+// Alphabet of the partition from its first record (SeqParser.Read on record 0 + GuessAlphabetLessConservatively,
+// bigseqkit-lib/helper.go:219-291), done on the host from a 256 KiB probe of the block.
+int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) {
+  ok = false;
+  const u32 probe = n < (256u << 10) ? n : (256u << 10);
+  h_probe_.reserve(probe + 16);
+  u8 *d = h_probe_.as<u8>();
+  BSK_CUDA(cudaMemcpyAsync(d, d_in, probe, cudaMemcpyDeviceToHost, stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  fastq = d[0] == '@';
+  const u8 marker = fastq ? '@' : '>';
+  // end of record 0 (exclusive): next record start, or EOF when the probe covers the whole block
+  u32 end = probe;
+  bool found = probe == n;
+  for (u32 L = 1; L < probe; L++) {
+    if (d[L - 1] != '\n' || d[L] != marker) continue;
+    if (fastq && L >= 3 && d[L - 3] == '\n' && d[L - 2] == '+') continue;
+    end = L;
+    found = true;
+    break;
+  }
+  if (!found) return BSK_OK;  // first record longer than the probe: not a short-record block
+  if (end > 0 && d[end - 1] == '\n') end--;  // ReadFixer strips one trailing newline
+  u32 p = 0;
+  while (p < end && d[p] != '\n') p++;  // header line
+  std::string seq;
+  const u32 limit = o_.AlphabetGuessSeqLength > 0 ? (u32)o_.AlphabetGuessSeqLength : 0xffffffffu;
+  if (p < end) {
+    p++;
+    bool in_qual = false;
+    while (p <= end && !in_qual) {
+      u32 q = p;
+      while (q < end && d[q] != '\n') q++;
+      const bool terminated = q < end;
+      if (fastq) {
+        if (!terminated) break;  // unterminated segment in sequence mode is dropped
+        if (q > p && d[p] == '+') { in_qual = true; break; }
+      }
+      if (seq.size() < limit) seq.append(reinterpret_cast<const char *>(d + p), q - p);
+      if (!terminated) break;
+      p = q + 1;
+    }
+  }
+  if (seq.size() > limit) seq.resize(limit);
+  u8 cm[256];
+  alphabet_class_masks(cm);
+  unsigned m = 0xffffffffu;
+  for (unsigned char c : seq) m &= cm[c];
+  first_guess_ = alphabet_from_mask(m, seq.empty());
+  if (alphabet_ == AB_NIL) alphabet_ = first_guess_;
+  alphabet_known_ = true;
+  ok = true;
+  return BSK_OK;
+}
+
+int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
+  if (n == 0) return kFusedFallback;
+  bool fastq = false, ok = false;
+  const int saved_alpha = alphabet_;
+  const bool saved_known = alphabet_known_;
+  if (!alphabet_known_ || first_block_) {
+    int rc = first_record_alphabet(d_in, n, fastq, ok);
+    if (rc != BSK_OK) return rc;
+    if (!ok) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; }
+  } else {
+    u8 *hs = h_small_.as<u8>();
+    BSK_CUDA(cudaMemcpyAsync(hs, d_in, 1, cudaMemcpyDeviceToHost, stream));
+    BSK_CUDA(cudaStreamSynchronize(stream));
+    fastq = hs[0] == '@';
+  }
+  EmitCfg cfg;
+  bool need_lut = false;
+  u8 *hl = h_small_.as<u8>() + 1024;
+  seq_emit_cfg(fastq, cfg, hl, need_lut);
+  if (!fastq && cfg.print_qual) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; }  // -q on FASTA: error path
+  reset_status();
+  BSK_CUDA(cudaMemcpyAsync(t_lut_, hl, 256, cudaMemcpyHostToDevice, stream));
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  // output can only grow through FASTA line wrapping: one '\n' per `width` bases, plus a final newline
+  size_t bound = (size_t)n + 64;
+  if (!fastq && cfg.width) bound += (size_t)n / cfg.width;
+  u8 *out = b_out_.get<u8>(bound);
+  u64 *elem = nullptr;
+  if (want_elem_off) elem = b_elem_.get<u64>((size_t)k::fused_max_records(n) + 2);
+  const size_t ts_bytes = k::fused_tile_state_bytes(n);
+  u8 *ts = b_tiles_.get<u8>(ts_bytes + 64);
+  BSK_CUDA(cudaMemsetAsync(ts, 0, ts_bytes + 64, stream));
+  u32 *ticket = reinterpret_cast<u32 *>(ts + ts_bytes);
+  main_begin();
+  k::seq_fused(d_in, n, out, elem, t_lut_, ts, ticket, d_status_, cfg, o_.OnlyId ? 1 : 0, fastq ? 1 : 0, o_.MinLen, o_.MaxLen,
+               stream);
+  main_end();
+  launches_++;
+  fetch_status();
+  if (h_status_->counters[0]) {  // some tile could not be handled: take the general path for the whole block
+    alphabet_ = saved_alpha;
+    alphabet_known_ = saved_known;
+    main_timed_ = false;
+    timings.main_launches--;
+    return kFusedFallback;
+  }
+  const u64 total = h_status_->counters[1], nrec = h_status_->counters[2], kept = h_status_->counters[3];
+  if (elem) {
+    u8 *hs = h_small_.as<u8>();
+    memcpy(hs, &total, 8);
+    BSK_CUDA(cudaMemcpyAsync(elem + kept, hs, 8, cudaMemcpyHostToDevice, stream));
+  }
+  fastq_ = fastq;
+  if (first_block_) part_fastq_ = fastq;
+  n_rec_ = (u32)nrec;
+  bo.d_data = out;
+  bo.n = total;
+  bo.d_elem_off = elem;
+  bo.n_elem = kept;
+  bo.n_rec = nrec;
+  if (nrec) any_record_ = true;
+  timings.fused_blocks++;
+  return BSK_OK;
+}
+
+}  // namespace bsk

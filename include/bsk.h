@@ -85,6 +85,7 @@ typedef struct {
   uint64_t main_launches;   /* launches of the dominant kernel summed in main_ms */
   uint64_t kernel_launches; /* launches of libbsk's own kernels in the last call */
   uint64_t in_bytes, out_bytes;
+  uint64_t fused_blocks;    /* blocks handled by the single-pass tile kernels (short-record path) */
 } bsk_timings;
 
 int bsk_version(void);
