@@ -27,7 +27,8 @@ Engine::Engine(Op op, const Opts &o, int device) : op_(op), o_(o), device_(devic
   t_qpow_ = reinterpret_cast<double *>(base + 1280);
   alphabet_ = o_.alphabet;
   alphabet_known_ = false;
-  fused_ok_ = getenv("BSK_NO_FUSED") == nullptr;  // debugging aid: force the general index/parse/emit path
+  fused_ok_ = getenv("BSK_NO_FUSED") == nullptr;      // debugging aid: force the general index/parse/emit path
+  inplace_ok_ = getenv("BSK_NO_INPLACE") == nullptr;  // debugging aid: skip the same-layout FASTQ kernel
 }
 
 Engine::~Engine() {

@@ -133,9 +133,14 @@ class Engine {
   // must take the general path instead
   static const int kFusedFallback = 1000;
   bool fused_ok_ = true;
+  bool inplace_ok_ = true;
   bool seq_fused_eligible() const;
   void seq_emit_cfg(bool fastq, EmitCfg &cfg, u8 *lut, bool &need_lut) const;
   int op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo);
+  // same-layout FASTQ kernel (k_fastq_inplace.cu); kFusedFallback when the block is outside its grammar
+  int op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg, const u8 *h_lut, bool need_lut, BlockOut &bo);
+  int n_sm_ = 0;
+  DevBuf b_tile_cnt_, b_tile_base_, b_slots_;
   int first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok);
   DevBuf b_tiles_;
   PinnedBuf h_probe_;

@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(FTHREADS) k_seq_fused(FusedSeqArgs a) {
   const u32 lim = (a.n - t0 < FT + FH) ? a.n - t0 : FT + FH;
   const bool eof_in_region = (a.n - t0) <= FT + FH;
   const u32 n_nl = sm.n_nl, n_rs = sm.n_rs;
-  const u32 first0 = tile == 0 ? 1u : 0u;  // virtual record start in front of the list
+  // a record that starts on the tile's first byte is announced by a newline in the look-behind, which the scan
+  // does not cover: tile 0 always owns offset 0, later tiles own it when the record-start rule holds at t0
+  u32 first0 = tile == 0 ? 1u : 0u;
+  if (tile > 0 && d[-1] == '\n' && d[0] == (fq ? '@' : '>') && !(fq && d[-3] == '\n' && d[-2] == '+')) first0 = 1u;
   // number of owned starts among rs[]: start position nl[rs[i]] + 1 < FT
   u32 n_own_rs = 0;
   if (!sm.fallback) {

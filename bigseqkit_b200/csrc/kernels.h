@@ -97,6 +97,14 @@ u32 fused_max_records(u32 n);
 void seq_fused(const u8 *in, u32 n, u8 *out, u64 *elem_off, const u8 *lut, void *tile_state, u32 *ticket, DevStatus *st,
                EmitCfg cfg, int only_id, int fastq, int min_len, int max_len, cudaStream_t s);
 
+// ---- FASTQ same-layout in-place kernel (k_fastq_inplace.cu): TMA-staged, no inter-CTA dependency
+u32 fastq_inplace_tiles(u32 n);
+u32 fastq_inplace_slot_stride();
+void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
+                   int use_lut, int n_sm, cudaStream_t s);
+void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles,
+                       cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

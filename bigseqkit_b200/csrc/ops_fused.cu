@@ -134,6 +134,15 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
   reset_status();
   BSK_CUDA(cudaMemcpyAsync(t_lut_, hl, 256, cudaMemcpyHostToDevice, stream));
   BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  // FASTQ, whole record printed, nothing dropped or renamed: the output record has the layout of the input record
+  if (inplace_ok_ && fastq && cfg.print_name && cfg.print_seq && cfg.print_qual && !o_.OnlyId && o_.MinLen <= 0 && o_.MaxLen <= 0) {
+    const int irc = op_seq_inplace(d_in, n, fastq, cfg, hl, need_lut, bo);
+    if (irc != kFusedFallback) {
+      if (irc != BSK_OK) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; }
+      return irc;
+    }
+    reset_status();
+  }
   // output can only grow through FASTA line wrapping: one '\n' per `width` bases, plus a final newline
   size_t bound = (size_t)n + 64;
   if (!fastq && cfg.width) bound += (size_t)n / cfg.width;
@@ -170,6 +179,58 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
   bo.n = total;
   bo.d_elem_off = elem;
   bo.n_elem = kept;
+  bo.n_rec = nrec;
+  if (nrec) any_record_ = true;
+  timings.fused_blocks++;
+  return BSK_OK;
+}
+
+// `seq` on FASTQ in same-layout mode: one streaming kernel + the element-offset expansion.
+int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg, const u8 *h_lut, bool need_lut, BlockOut &bo) {
+  (void)h_lut;
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    int dev = device_ >= 0 ? device_ : 0;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  const u32 n_tiles = k::fastq_inplace_tiles(n);
+  u8 *out = b_out_.get<u8>((size_t)n + 64);
+  u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
+  u16 *slots = b_slots_.get<u16>((size_t)n_tiles * k::fastq_inplace_slot_stride());
+  BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
+  main_begin();
+  k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, n_sm_, stream);
+  main_end();
+  launches_++;
+  u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
+  prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  u8 *hs = h_small_.as<u8>();
+  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  fetch_status();  // synchronises the stream
+  if (h_status_->counters[0]) {
+    main_timed_ = false;
+    timings.main_launches--;
+    return kFusedFallback;
+  }
+  u64 nrec;
+  memcpy(&nrec, hs, 8);
+  const u64 total = h_status_->counters[1];
+  u64 *elem = nullptr;
+  if (want_elem_off) {
+    elem = b_elem_.get<u64>((size_t)nrec + 2);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, stream);
+    launches_++;
+    memcpy(hs + 16, &total, 8);
+    BSK_CUDA(cudaMemcpyAsync(elem + nrec, hs + 16, 8, cudaMemcpyHostToDevice, stream));
+  }
+  fastq_ = fastq;
+  if (first_block_) part_fastq_ = fastq;
+  n_rec_ = (u32)nrec;
+  bo.d_data = out;
+  bo.n = total;
+  bo.d_elem_off = elem;
+  bo.n_elem = nrec;
   bo.n_rec = nrec;
   if (nrec) any_record_ = true;
   timings.fused_blocks++;

@@ -103,3 +103,96 @@ def test_fused_multi_block_partition(lib, monkeypatch):
     r, t = run(lib, data, opts)
     assert r.data == exp[0] and list(r.elem_off) == exp[1]
     assert t["fused_blocks"] >= 4
+
+
+# ---------------------------------------------------------------- same-layout FASTQ kernel (k_fastq_inplace.cu)
+def _fixed_fastq(n_rec, hdr_len, seq_len, seed, alphabet="ACGTN", plus=""):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n_rec):
+        h = ("%0*d" % (hdr_len, i))[-hdr_len:] if hdr_len else ""
+        s = "".join(rng.choice(alphabet) for _ in range(seq_len))
+        q = "".join(chr(rng.randint(33, 74)) for _ in range(seq_len))
+        out.append("@%s\n%s\n+%s\n%s\n" % (h, s, plus, q))
+    return "".join(out).encode()
+
+
+INPLACE_OPTS = [
+    {"Reverse": True, "Complement": True},
+    {"Reverse": True},
+    {"Complement": True},
+    {},
+    {"Name": True, "Seq": True, "Reverse": True, "Complement": True, "LowerCase": True},
+    {"Dna2rna": True, "Reverse": True},
+]
+
+
+def inplace_inputs():
+    return {
+        # 64-byte records: every 16 KiB / 20 KiB tile boundary is a record start
+        "rec64_tile_aligned": _fixed_fastq(2000, 8, 25, 21),
+        # records of 1 KiB: tile boundaries fall at every phase of a record, starts on boundaries included
+        "rec1024": _fixed_fastq(150, 10, 504, 22),
+        "reads150": synth.fastq_reads(400 << 10, seed=23).tobytes(),
+        "iupac_lower": _fixed_fastq(700, 12, 151, 24, alphabet="ACGTNacgtnRYKMSWBDHVrykm"),
+        "no_final_newline": synth.fastq_reads(90 << 10, seed=25).tobytes()[:-1],
+        "len250": _fixed_fastq(400, 30, 250, 26),        # 63-64 words per segment: register path at its limit
+        "len251_to_600": b"".join(_fixed_fastq(1, 20, 251 + 7 * i, 100 + i) for i in range(50)),  # byte-pair path
+        "empty_seq_and_header": b"@\n\n+\n\n@a\nA\n+\nI\n" * 300,
+        "qual_starts_with_at_and_plus": b"@r\nACGT\n+\n@+@+\n@s\nGG\n+\n+@\n" * 300,
+        "tiny_file": b"@a\nACGT\n+\nIIII\n",
+        "tiny_file_no_nl": b"@a\nAC\n+\nII",
+    }
+
+
+@pytest.mark.parametrize("opts", INPLACE_OPTS, ids=lambda o: str(o)[:50])
+def test_inplace_parity(lib, opts):
+    for name, data in inplace_inputs().items():
+        exp = oracle.seq(data, opts)
+        r, t = run(lib, data, opts)
+        assert r.data == exp[0], (name, opts)
+        assert list(r.elem_off) == exp[1], (name, opts)
+        assert t["fused_blocks"] == 1 and t["kernel_launches"] == 2, (name, opts, t)
+
+
+INPLACE_OUTSIDE_GRAMMAR = {
+    "plus_with_name": _fixed_fastq(300, 9, 80, 31, plus="x y"),
+    "one_plus_with_name_late": _fixed_fastq(900, 9, 80, 32) + b"@z\nAC\n+z\nII\n" + _fixed_fastq(50, 9, 80, 33),
+    "record_longer_than_halo": _fixed_fastq(3, 5, 6000, 34) + _fixed_fastq(200, 9, 80, 35),
+    "multiline_in_the_middle": _fixed_fastq(400, 9, 80, 36) + b"@m\nACGT\nAC\n+\nIIII\nII\n" + _fixed_fastq(10, 9, 80, 37),
+    "seq_line_starts_with_plus": _fixed_fastq(100, 9, 80, 38) + b"@p\n+CGT\n+\nIIII\n",
+    "missing_first_marker": b"ACGT\n+\nIIII\n" + _fixed_fastq(100, 9, 80, 39),
+    "trailing_blank_line": _fixed_fastq(100, 9, 80, 40) + b"\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(INPLACE_OUTSIDE_GRAMMAR))
+def test_inplace_leaves_other_grammars_to_the_general_paths(lib, name):
+    data = INPLACE_OUTSIDE_GRAMMAR[name]
+    opts = {"Reverse": True, "Complement": True}
+    try:
+        exp, exp_err = oracle.seq(data, opts), None
+    except oracle.OracleError as e:
+        exp, exp_err = None, str(e)
+    try:
+        (r, t), err = run(lib, data, opts), None
+    except Exception as e:  # noqa: BLE001
+        r, t, err = None, None, str(e)
+    assert err == exp_err, name
+    if exp is not None:
+        assert r.data == exp[0] and list(r.elem_off) == exp[1], name
+
+
+def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
+    # regression: a record whose first byte is the first byte of a 16 KiB tile was dropped by k_seq_fused
+    monkeypatch.setenv("BSK_NO_INPLACE", "1")
+    data = _fixed_fastq(2000, 8, 25, 41)
+    for opts in ({"Reverse": True, "Complement": True}, {"MinLen": 5}, {"Name": True}):
+        exp = oracle.seq(data, opts)
+        r, t = run(lib, data, opts)
+        assert r.data == exp[0] and list(r.elem_off) == exp[1]
+        assert t["fused_blocks"] == 1 and t["kernel_launches"] == 1
+    fa = b"".join(b">%05d\n%s\n" % (i, b"ACGTACGTAC" * 5 + b"ACGTAC") for i in range(2000))  # 64-byte FASTA records
+    exp = oracle.seq(fa, {"Complement": True})
+    r, t = run(lib, fa, {"Complement": True})
+    assert r.data == exp[0] and list(r.elem_off) == exp[1] and t["fused_blocks"] == 1

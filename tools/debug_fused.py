@@ -14,7 +14,7 @@ for rep in range(reps):
         t = op.timings()
     ok_d = got.data == exp
     ok_o = list(got.elem_off) == exp_off
-    print("rep", rep, "data_ok", ok_d, "off_ok", ok_o, "n", len(got.data), len(exp), "n_elem", got.n_elem, len(exp_off) - 1,
+    print("rep", rep, "data_ok", ok_d, "off_ok", ok_o, "n", len(got.data), len(exp), "n_elem", len(got.elem_off) - 1, len(exp_off) - 1,
           "fused", t["fused_blocks"], "launches", t["kernel_launches"], flush=True)
     if not ok_d:
         g = got.data

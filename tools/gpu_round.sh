@@ -3,7 +3,7 @@
 # usage (on the GPU box, from the repo root): bash tools/gpu_round.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r1}
-KRE=${2:-k_seq_fused}
+KRE=${2:-k_fastq_inplace}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
