@@ -154,6 +154,10 @@ static inline unsigned __vcmpgeu4(unsigned a, unsigned b) {
     if (((a >> (8 * i)) & 0xff) >= ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
   return r;
 }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
+  return c;
+}
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
   return (unsigned long long)(((unsigned __int128)a * b) >> 64);
 }

@@ -41,8 +41,6 @@ constexpr u32 STAGE = PRE + T + H + 16;
 constexpr u32 NSTAGE = 3;
 constexpr u32 LCAP = 3072;     // line starts per region
 constexpr u32 RCAP = 512;      // owned records per tile (slot stride)
-constexpr u32 G = 16;          // lanes per record in the transform
-constexpr u32 WPL = 4;         // words per lane held in registers by the in-place reversal
 static_assert((T + H) / 16 == NWARP * 32 * CPL, "scan partition must cover the region exactly");
 static_assert(STAGE % 16 == 0, "stage size");
 
@@ -69,6 +67,7 @@ struct FqInplaceArgs {
   DevStatus *st;   // counters[0] = fallback flag
   u32 n_tiles;
   int reverse, use_lut;
+  int group;       // lanes per record in the transform: 8 (records <= ~250 B per segment), 16, 32
 };
 
 // flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value
@@ -83,56 +82,61 @@ __device__ __forceinline__ u32 lut4(const u8 *lut, u32 v) {
          ((u32)lut[v >> 24] << 24);
 }
 
-// In-place rewrite of the byte range [a, a + L) of the region (d = region byte 0, 4-byte aligned) by the
-// 16 lanes of a half-warp: optional reversal, optional byte map.  Every lane of the warp must call it.
-template <bool REV, bool LUT>
+// In-place rewrite of the byte range [a, a + L) of the region (d = region byte 0, 4-byte aligned) by a group
+// of G lanes: optional reversal, optional byte map.  Whole 32-bit words inside the range are produced with one
+// PRMT from two source words (registers hold the segment until every lane has read); the <= 3 ragged bytes at
+// each end go through a byte path on lanes 0-5 of the group.  Every lane of the warp must call it.
+template <bool REV, bool LUT, u32 G, u32 WPL>
 __device__ __forceinline__ void seg_inplace(u8 *d, u32 a, u32 L, const u8 *lut, u32 gl) {
   u32 *w32 = reinterpret_cast<u32 *>(d);
-  const int W0 = (int)(a >> 2);
-  const u32 nw = L ? ((a + L - 1) >> 2) - (a >> 2) + 1 : 0;
-  const bool slow = __any_sync(0xffffffffu, nw > fq::G * fq::WPL);
+  const u32 e = a + L;
+  const u32 ai = (a + 3u) & ~3u, ae = e & ~3u;          // word-aligned interior [ai, ae)
+  const u32 nwf = ae > ai ? (ae - ai) >> 2 : 0u;
+  const bool slow = __any_sync(0xffffffffu, nwf > G * WPL);
   if (!slow) {
-    u32 vals[fq::WPL];
+    // ragged bytes: lanes 0-2 the head [a, min(ai, e)), lanes 3-5 the tail [max(ae, ai), e)
+    const u32 head_end = ai < e ? ai : e;
+    const u32 tail_beg = ae > ai ? ae : (ai < e ? ai : e);
+    u32 x = gl < 3u ? a + gl : tail_beg + (gl - 3u);
+    const bool eok = gl < 3u ? x < head_end : (gl < 6u && x < e);
+    u8 ev = 0;
+    if (eok) {
+      ev = d[REV ? (a + e - 1u - x) : x];
+      if (LUT) ev = lut[ev];
+    }
+    u32 vals[WPL];
+    const u32 U0 = a + e - 4u - ai;  // lowest source byte of interior word 0 (dest byte ai+b <- source U0+3-b)
+    const u32 sh = U0 & 3u;
+    const u32 sel = (sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12);
+    const u32 q0 = U0 >> 2, wi = ai >> 2;
 #pragma unroll
-    for (u32 j = 0; j < fq::WPL; j++) {
-      const u32 idx = gl + j * fq::G;
+    for (u32 j = 0; j < WPL; j++) {
+      const u32 idx = gl + j * G;
       u32 v = 0;
-      if (idx < nw) {
-        const int A = (W0 + (int)idx) * 4;  // first byte of the destination word (may be < a)
+      if (idx < nwf) {
         if (REV) {
-          const int U = (int)(2 * a + L) - 4 - A;  // lowest source byte: dest byte A+b <- source U+3-b
-          const int q = U >> 2;
-          const u32 sh = (u32)U & 3u;
-          const u32 lo = w32[q], hi = w32[q + 1];
-          v = __byte_perm(lo, hi, (sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12));
+          const u32 lo = w32[q0 - idx], hi = w32[q0 - idx + 1u];
+          v = __byte_perm(lo, hi, sel);
         } else {
-          v = w32[W0 + (int)idx];
+          v = w32[wi + idx];
         }
         if (LUT) v = lut4(lut, v);
-        const u32 lo_ok = A < (int)a ? a - (u32)A : 0u;                          // bytes [lo_ok, hi_ok) are inside
-        const u32 hi_ok = (u32)A + 4u > a + L ? a + L - (u32)A : 4u;
-        if (lo_ok != 0u || hi_ok != 4u) {
-          u32 m = 0xffffffffu;
-          if (lo_ok) m &= 0xffffffffu << (8u * lo_ok);
-          if (hi_ok < 4u) m &= 0xffffffffu >> (8u * (4u - hi_ok));
-          const u32 old = w32[W0 + (int)idx];
-          v = (v & m) | (old & ~m);
-        }
       }
       vals[j] = v;
     }
     __syncwarp();
 #pragma unroll
-    for (u32 j = 0; j < fq::WPL; j++) {
-      const u32 idx = gl + j * fq::G;
-      if (idx < nw) w32[W0 + (int)idx] = vals[j];
+    for (u32 j = 0; j < WPL; j++) {
+      const u32 idx = gl + j * G;
+      if (idx < nwf) w32[wi + idx] = vals[j];
     }
+    if (eok) d[x] = ev;
     __syncwarp();
   } else {
     // long segment: independent byte pairs (i, L-1-i), no hazards
     if (REV) {
       const u32 half = L >> 1;
-      for (u32 i = gl; i < half; i += fq::G) {
+      for (u32 i = gl; i < half; i += G) {
         u8 x = d[a + i], y = d[a + L - 1 - i];
         if (LUT) { x = lut[x]; y = lut[y]; }
         d[a + i] = y;
@@ -140,9 +144,32 @@ __device__ __forceinline__ void seg_inplace(u8 *d, u32 a, u32 L, const u8 *lut, 
       }
       if (LUT && (L & 1u) && gl == 0) d[a + half] = lut[d[a + half]];
     } else if (LUT) {
-      for (u32 i = gl; i < L; i += fq::G) d[a + i] = lut[d[a + i]];
+      for (u32 i = gl; i < L; i += G) d[a + i] = lut[d[a + i]];
     }
     __syncwarp();
+  }
+}
+
+// transform of all owned records of a tile, G lanes per record
+template <u32 G, u32 WPL>
+__device__ __forceinline__ void transform_tile(fq::Smem &sm, u8 *d, u32 n_own, int reverse, int use_lut) {
+  const u32 g = threadIdx.x / G, gl = threadIdx.x % G;
+  for (u32 rb = 0; rb < n_own; rb += fq::NT / G) {  // uniform trip count per CTA
+    const u32 r = rb + g;
+    u32 so = 0, sl = 0, qo = 0;
+    if (r < n_own) {
+      const u32 k = sm.r_line[r];
+      so = sm.ls[k + 1];
+      sl = sm.ls[k + 2] - 1u - so;
+      qo = sm.ls[k + 3];
+    }
+    if (reverse) {
+      if (use_lut) seg_inplace<true, true, G, WPL>(d, so, sl, sm.lut, gl);
+      else seg_inplace<true, false, G, WPL>(d, so, sl, sm.lut, gl);
+      seg_inplace<true, false, G, WPL>(d, qo, sl, sm.lut, gl);
+    } else {
+      seg_inplace<false, true, G, WPL>(d, so, sl, sm.lut, gl);
+    }
   }
 }
 
@@ -212,25 +239,30 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
       __syncthreads();
     }
 
-    // ---- newline scan: lane owns CPL consecutive 16-byte chunks
-    const u32 c0 = (warp * 32u + lane) * CPL;
-    u32 f[CPL][4];
-    u32 cnt = 0;
+    // ---- newline scan: lane owns CPL consecutive 16-byte chunks; the 0x80 flag bytes of a chunk are packed into a
+    // position-ordered 16-bit mask with four IDP.4A (flag byte * {1,2,4,8} summed = nibble << 7)
+    const u32 span = (warp * 32u + lane) * (CPL * 16u);
+    u32 mlo, mhi;
+    {
+      u32 m16[CPL];
 #pragma unroll
-    for (u32 j = 0; j < CPL; j++) {
-      const u32 p = (c0 + j) * 16u;
-      const uint4 v = *reinterpret_cast<const uint4 *>(d + p);
-      f[j][0] = nl_flags(v.x); f[j][1] = nl_flags(v.y); f[j][2] = nl_flags(v.z); f[j][3] = nl_flags(v.w);
-      if (p + 16u > lim) {  // bytes past the end of the file do not count
-#pragma unroll
-        for (u32 q = 0; q < 4; q++) {
-          const u32 b0 = p + 4u * q;
-          if (b0 >= lim) f[j][q] = 0;
-          else if (b0 + 4u > lim) f[j][q] &= 0xffffffffu >> (8u * (b0 + 4u - lim));
-        }
+      for (u32 j = 0; j < CPL; j++) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(d + span + j * 16u);
+        u32 lo = __dp4a(nl_flags(v.x), 0x08040201u, 0u);
+        lo = __dp4a(nl_flags(v.y), 0x80402010u, lo);
+        u32 hi = __dp4a(nl_flags(v.z), 0x08040201u, 0u);
+        hi = __dp4a(nl_flags(v.w), 0x80402010u, hi);
+        m16[j] = (lo >> 7) | (hi << 1);
       }
-      cnt += __popc(f[j][0]) + __popc(f[j][1]) + __popc(f[j][2]) + __popc(f[j][3]);
+      mlo = m16[0] | (m16[1] << 16);
+      mhi = m16[2];
     }
+    if (span + CPL * 16u > lim) {  // bytes past the end of the file do not count
+      const u32 valid = lim > span ? lim - span : 0u;
+      if (valid < 32u) { mlo &= (1u << valid) - 1u; mhi = 0; }
+      else mhi &= (1u << (valid - 32u)) - 1u;
+    }
+    const u32 cnt = __popc(mlo) + __popc(mhi);
     u32 inc = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -240,28 +272,31 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
     if (lane == 31) sm.wtot[warp] = inc;
     if (tid == 0) sm.bad = 0;
     __syncthreads();
-    u32 base = 0, n_nl = 0;
+    u32 base, n_nl;
+    {
+      u32 x = sm.wtot[lane & (NWARP - 1u)];
 #pragma unroll
-    for (u32 w = 0; w < NWARP; w++) {
-      const u32 t = sm.wtot[w];
-      if (w < warp) base += t;
-      n_nl += t;
+      for (int off = 1; off < (int)NWARP; off <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, x, off, NWARP);
+        if ((int)(lane & (NWARP - 1u)) >= off) x += y;
+      }
+      n_nl = __shfl_sync(0xffffffffu, x, NWARP - 1u);
+      base = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
+      if (warp == 0) base = 0;
     }
     const bool virt = eof && lim > 0 && d[lim - 1] != '\n';  // unterminated last line
     const bool overflow = n_nl + 2 > LCAP;
     if (!overflow) {
       u32 k = base + inc - cnt + 1;  // ls[k] = start of the line after the (k-1)-th newline
-#pragma unroll
-      for (u32 j = 0; j < CPL; j++) {
-#pragma unroll
-        for (u32 q = 0; q < 4; q++) {
-          u32 m = f[j][q];
-          while (m) {
-            const u32 b = (u32)(__ffs((int)m) - 1) >> 3;
-            m &= m - 1;
-            sm.ls[k++] = (u16)((c0 + j) * 16u + 4u * q + b + 1u);
-          }
-        }
+      while (mlo) {
+        const u32 t = (u32)__ffs((int)mlo) - 1u;
+        mlo &= mlo - 1u;
+        sm.ls[k++] = (u16)(span + t + 1u);
+      }
+      while (mhi) {
+        const u32 t = (u32)__ffs((int)mhi) - 1u;
+        mhi &= mhi - 1u;
+        sm.ls[k++] = (u16)(span + 32u + t + 1u);
       }
       if (tid == 0) {
         sm.ls[0] = 0;
@@ -308,12 +343,17 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
       const u32 bal = __ballot_sync(0xffffffffu, own);
       if (lane == 0) sm.wtot2[warp] = __popc(bal);
       __syncthreads();
-      u32 wb = 0, tot = 0;
+      u32 wb, tot;
+      {
+        u32 x = sm.wtot2[lane & (NWARP - 1u)];
 #pragma unroll
-      for (u32 w = 0; w < NWARP; w++) {
-        const u32 t = sm.wtot2[w];
-        if (w < warp) wb += t;
-        tot += t;
+        for (int off = 1; off < (int)NWARP; off <<= 1) {
+          const u32 y = __shfl_up_sync(0xffffffffu, x, off, NWARP);
+          if ((int)(lane & (NWARP - 1u)) >= off) x += y;
+        }
+        tot = __shfl_sync(0xffffffffu, x, NWARP - 1u);
+        wb = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
+        if (warp == 0) wb = 0;
       }
       if (own) {
         const u32 r = run + wb + __popc(bal & ((1u << lane) - 1u));
@@ -335,24 +375,9 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
     for (u32 r = tid; r < n_own; r += NT) a.slots[(size_t)tile * RCAP + r] = sm.ls[sm.r_line[r]];
     if (tid == 0) a.tile_cnt[tile] = n_own;
     if (a.reverse || a.use_lut) {
-      const u32 g = tid / G, gl = tid % G;
-      for (u32 rb = 0; rb < n_own; rb += NT / G) {  // uniform trip count per CTA
-        const u32 r = rb + g;
-        u32 so = 0, sl = 0, qo = 0;
-        if (r < n_own) {
-          const u32 k = sm.r_line[r];
-          so = sm.ls[k + 1];
-          sl = sm.ls[k + 2] - 1u - so;
-          qo = sm.ls[k + 3];
-        }
-        if (a.reverse) {
-          if (a.use_lut) seg_inplace<true, true>(d, so, sl, sm.lut, gl);
-          else seg_inplace<true, false>(d, so, sl, sm.lut, gl);
-          seg_inplace<true, false>(d, qo, sl, sm.lut, gl);
-        } else {
-          seg_inplace<false, true>(d, so, sl, sm.lut, gl);
-        }
-      }
+      if (a.group == 8) transform_tile<8, 8>(sm, d, n_own, a.reverse, a.use_lut);
+      else if (a.group == 16) transform_tile<16, 4>(sm, d, n_own, a.reverse, a.use_lut);
+      else transform_tile<32, 4>(sm, d, n_own, a.reverse, a.use_lut);
     }
     tma::fence_proxy_async();
     __syncthreads();
@@ -397,7 +422,7 @@ u32 fastq_inplace_tiles(u32 n) { return (n + fq::T - 1) / fq::T; }
 u32 fastq_inplace_slot_stride() { return fq::RCAP; }
 
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
-                   int use_lut, int n_sm, cudaStream_t s) {
+                   int use_lut, int group, int n_sm, cudaStream_t s) {
   FqInplaceArgs a;
   a.in = in;
   a.n = n;
@@ -409,6 +434,7 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   a.n_tiles = fastq_inplace_tiles(n);
   a.reverse = reverse;
   a.use_lut = use_lut;
+  a.group = group;
   const size_t smem = sizeof(fq::Smem) + 16;
 #ifndef BSK_EMU
   static bool attr_set = false;

@@ -1,4 +1,5 @@
 // ops_fused.cu -- host side of the single-pass tile path (k_fused.cu) for `seq` on short records.
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -99,6 +100,7 @@ int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) 
       p = q + 1;
     }
   }
+  first_seq_len_ = (u32)seq.size();
   if (seq.size() > limit) seq.resize(limit);
   u8 cm[256];
   alphabet_class_masks(cm);
@@ -200,7 +202,12 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   u16 *slots = b_slots_.get<u16>((size_t)n_tiles * k::fastq_inplace_slot_stride());
   BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
   main_begin();
-  k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, n_sm_, stream);
+  // lanes per record: 8 lanes x 8 words hold segments up to ~256 B (reads), 32 x 4 up to ~512 B; longer ones take
+  // the byte-pair path inside the kernel
+  int group = first_seq_len_ <= 250 ? 8 : 32;
+  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : atoi(e) == 16 ? 16 : 32;
+  k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group, n_sm_,
+                   stream);
   main_end();
   launches_++;
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);

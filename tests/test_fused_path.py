@@ -196,3 +196,15 @@ def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
     exp = oracle.seq(fa, {"Complement": True})
     r, t = run(lib, fa, {"Complement": True})
     assert r.data == exp[0] and list(r.elem_off) == exp[1] and t["fused_blocks"] == 1
+
+
+@pytest.mark.parametrize("group", ["8", "16", "32"])
+def test_inplace_lane_group_variants(lib, monkeypatch, group):
+    monkeypatch.setenv("BSK_FQ_GROUP", group)
+    opts = {"Reverse": True, "Complement": True}
+    for name in ("reads150", "len250", "len251_to_600", "rec64_tile_aligned", "empty_seq_and_header"):
+        data = inplace_inputs()[name]
+        exp = oracle.seq(data, opts)
+        r, t = run(lib, data, opts)
+        assert r.data == exp[0] and list(r.elem_off) == exp[1], (name, group)
+        assert t["fused_blocks"] == 1 and t["kernel_launches"] == 2
