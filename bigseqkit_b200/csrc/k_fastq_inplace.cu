@@ -24,6 +24,8 @@
 // Anything outside the grammar (multi-line records, "+name" lines, missing marker, blank lines, records
 // longer than the halo, unmatched lengths) raises a flag and the caller re-runs the block on the general
 // path, which also produces the reference's error text.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tma.cuh"
 
@@ -31,30 +33,34 @@ namespace bsk {
 namespace k {
 
 namespace fq {
-constexpr u32 T = 20480;       // tile bytes
-constexpr u32 H = 4096;        // halo bytes
+constexpr u32 H = 4096;        // halo bytes (longest record the kernel accepts, roughly)
 constexpr u32 PRE = 16;        // look-behind bytes in front of the tile
-constexpr u32 NT = 512;        // threads per CTA
-constexpr u32 NWARP = NT / 32;
-constexpr u32 CPL = 3;         // 16-byte chunks per lane in the newline scan
-constexpr u32 STAGE = PRE + T + H + 16;
 constexpr u32 NSTAGE = 3;
 constexpr u32 LCAP = 3072;     // line starts per region
 constexpr u32 RCAP = 512;      // owned records per tile (slot stride)
-static_assert((T + H) / 16 == NWARP * 32 * CPL, "scan partition must cover the region exactly");
-static_assert(STAGE % 16 == 0, "stage size");
 
-struct Smem {
-  u8 in[NSTAGE][STAGE];
-  u64 full[NSTAGE];
-  u8 lut[256];
-  u16 ls[LCAP + 8];     // line starts, ls[0] = 0
-  u8 isrs[LCAP + 8];    // line k opens a record
-  u16 r_line[RCAP];     // first line of every owned record, in input order
-  u32 wtot[NWARP];
-  u32 wtot2[NWARP];
-  u32 bad;
+// CTA shape: NT threads, every lane scans CPL consecutive 16-byte chunks, so tile + halo = NT * CPL * 16 bytes
+template <u32 NT_, u32 CPL_, u32 CTAS_>
+struct Cfg {
+  static constexpr u32 NT = NT_, CPL = CPL_, CTAS = CTAS_;
+  static constexpr u32 NWARP = NT / 32;
+  static constexpr u32 T = NT * CPL * 16 - H;                 // tile bytes
+  static constexpr u32 STAGE = PRE + T + H + 16;
+  static constexpr u32 LITER = (LCAP + NT) / NT;              // passes of the CTA over the line list
+  static_assert(T % 16 == 0 && STAGE % 16 == 0 && T + H < 32768, "tile geometry");
+  struct Smem {
+    u8 in[NSTAGE][STAGE];
+    u64 full[NSTAGE];
+    u8 lut[256];
+    u16 ls[LCAP + 8];          // line starts (bit 15: the line opens a record), ls[0] = 0
+    u16 r_line[RCAP];          // first line of every owned record, any order
+    u32 wtot[NWARP];
+    u32 wtot2[LITER][NWARP];   // owned records per (pass over the line list, warp)
+    u32 bad, rescan, n_list, kmin, kmax;
+  };
 };
+typedef Cfg<512, 3, 2> CfgA;   // 20 KiB tiles, 2 CTAs / SM
+typedef Cfg<256, 4, 4> CfgB;   // 12 KiB tiles, 4 CTAs / SM: smaller barrier domains, more phase diversity per SM
 }  // namespace fq
 
 struct FqInplaceArgs {
@@ -68,6 +74,9 @@ struct FqInplaceArgs {
   u32 n_tiles;
   int reverse, use_lut;
   int group;       // lanes per record in the transform: 8 (records <= ~250 B per segment), 16, 32
+  int wpl;         // group == 8: words per lane (5 covers segments up to 160 B, else 8)
+  int issue_late;  // refill the ring after the grammar check (default) instead of at the top of the tile (BSK_FQ_EARLY)
+  u32 scan_halo;   // bytes of the halo the newline scan covers on its first attempt (multiple of 16, <= H)
 };
 
 // flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value
@@ -82,99 +91,121 @@ __device__ __forceinline__ u32 lut4(const u8 *lut, u32 v) {
          ((u32)lut[v >> 24] << 24);
 }
 
-// In-place rewrite of the byte range [a, a + L) of the region (d = region byte 0, 4-byte aligned) by a group
-// of G lanes: optional reversal, optional byte map.  Whole 32-bit words inside the range are produced with one
-// PRMT from two source words (registers hold the segment until every lane has read); the <= 3 ragged bytes at
-// each end go through a byte path on lanes 0-5 of the group.  Every lane of the warp must call it.
-template <bool REV, bool LUT, u32 G, u32 WPL>
-__device__ __forceinline__ void seg_inplace(u8 *d, u32 a, u32 L, const u8 *lut, u32 gl) {
-  u32 *w32 = reinterpret_cast<u32 *>(d);
-  const u32 e = a + L;
-  const u32 ai = (a + 3u) & ~3u, ae = e & ~3u;          // word-aligned interior [ai, ae)
-  const u32 nwf = ae > ai ? (ae - ai) >> 2 : 0u;
-  const bool slow = __any_sync(0xffffffffu, nwf > G * WPL);
-  if (!slow) {
-    // ragged bytes: lanes 0-2 the head [a, min(ai, e)), lanes 3-5 the tail [max(ae, ai), e)
-    const u32 head_end = ai < e ? ai : e;
-    const u32 tail_beg = ae > ai ? ae : (ai < e ? ai : e);
-    u32 x = gl < 3u ? a + gl : tail_beg + (gl - 3u);
-    const bool eok = gl < 3u ? x < head_end : (gl < 6u && x < e);
-    u8 ev = 0;
-    if (eok) {
-      ev = d[REV ? (a + e - 1u - x) : x];
-      if (LUT) ev = lut[ev];
-    }
-    u32 vals[WPL];
+// Word geometry of the in-place rewrite of the byte range [a, e): whole 32-bit words [ai, ae) are produced with
+// one PRMT from two source words, the <= 3 ragged bytes at each end go through a byte path.
+struct SegGeo {
+  u32 a, e, nwf, sel, q0, wi;
+  __device__ __forceinline__ SegGeo(u32 a_, u32 L) {
+    a = a_;
+    e = a_ + L;
+    const u32 ai = (a + 3u) & ~3u, ae = e & ~3u;
+    nwf = ae > ai ? (ae - ai) >> 2 : 0u;
     const u32 U0 = a + e - 4u - ai;  // lowest source byte of interior word 0 (dest byte ai+b <- source U0+3-b)
     const u32 sh = U0 & 3u;
-    const u32 sel = (sh + 3u) | ((sh + 2u) << 4) | ((sh + 1u) << 8) | (sh << 12);
-    const u32 q0 = U0 >> 2, wi = ai >> 2;
+    sel = 0x0123u + sh * 0x1111u;    // PRMT selector {sh+3, sh+2, sh+1, sh}
+    q0 = U0 >> 2;
+    wi = ai >> 2;
+  }
+  // ragged byte handled by lane t of the group (t < 3: head, 3 <= t < 6: tail); false when there is none
+  __device__ __forceinline__ bool edge(u32 t, u32 &x) const {
+    const u32 ai = wi << 2, ae = e & ~3u;
+    const u32 head_end = ai < e ? ai : e;
+    const u32 tail_beg = ae > ai ? ae : head_end;
+    x = t < 3u ? a + t : tail_beg + (t - 3u);
+    return t < 3u ? x < head_end : (t < 6u && x < e);
+  }
+};
+
+// In-place rewrite of one record by a group of G lanes: sequence [so, so+sl) reversed (REV) and mapped through
+// lut (LUT), quality [qo, qo+sl) reversed (REV).  Registers hold both segments until every lane has read, so the
+// rewrite is hazard-free; segments longer than G*WPL words take independent byte pairs.  Every lane of the warp
+// must call it (inactive groups pass sl = 0).
+template <bool REV, bool LUT, u32 G, u32 WPL>
+__device__ __forceinline__ void record_inplace(u8 *d, u32 so, u32 sl, u32 qo, const u8 *lut, u32 gl) {
+  u32 *w32 = reinterpret_cast<u32 *>(d);
+  const SegGeo S(so, sl), Q(qo, sl);
+  const bool slow = __any_sync(0xffffffffu, S.nwf > G * WPL || Q.nwf > G * WPL);
+  if (!slow) {
+    u32 xs, xq = 0;
+    const bool es = S.edge(gl, xs);
+    const bool eq = REV && Q.edge(gl, xq);
+    u8 vs = 0, vq = 0;
+    if (es) {
+      vs = d[REV ? (S.a + S.e - 1u - xs) : xs];
+      if (LUT) vs = lut[vs];
+    }
+    if (eq) vq = d[Q.a + Q.e - 1u - xq];
+    u32 sv[WPL], qv[WPL];
 #pragma unroll
     for (u32 j = 0; j < WPL; j++) {
       const u32 idx = gl + j * G;
-      u32 v = 0;
-      if (idx < nwf) {
-        if (REV) {
-          const u32 lo = w32[q0 - idx], hi = w32[q0 - idx + 1u];
-          v = __byte_perm(lo, hi, sel);
-        } else {
-          v = w32[wi + idx];
-        }
-        if (LUT) v = lut4(lut, v);
+      sv[j] = 0;
+      qv[j] = 0;
+      if (idx < S.nwf) {
+        if (REV) sv[j] = __byte_perm(w32[S.q0 - idx], w32[S.q0 - idx + 1u], S.sel);
+        else sv[j] = w32[S.wi + idx];
       }
-      vals[j] = v;
+      if (REV && idx < Q.nwf) qv[j] = __byte_perm(w32[Q.q0 - idx], w32[Q.q0 - idx + 1u], Q.sel);
+      if (LUT && idx < S.nwf) sv[j] = lut4(lut, sv[j]);
     }
     __syncwarp();
 #pragma unroll
     for (u32 j = 0; j < WPL; j++) {
       const u32 idx = gl + j * G;
-      if (idx < nwf) w32[wi + idx] = vals[j];
+      if (idx < S.nwf) w32[S.wi + idx] = sv[j];
+      if (REV && idx < Q.nwf) w32[Q.wi + idx] = qv[j];
     }
-    if (eok) d[x] = ev;
+    if (es) d[xs] = vs;
+    if (eq) d[xq] = vq;
     __syncwarp();
   } else {
-    // long segment: independent byte pairs (i, L-1-i), no hazards
+    // long segments: independent byte pairs (i, L-1-i), no hazards
     if (REV) {
-      const u32 half = L >> 1;
+      const u32 half = sl >> 1;
       for (u32 i = gl; i < half; i += G) {
-        u8 x = d[a + i], y = d[a + L - 1 - i];
+        u8 x = d[so + i], y = d[so + sl - 1 - i];
         if (LUT) { x = lut[x]; y = lut[y]; }
-        d[a + i] = y;
-        d[a + L - 1 - i] = x;
+        d[so + i] = y;
+        d[so + sl - 1 - i] = x;
+        const u8 p = d[qo + i], q = d[qo + sl - 1 - i];
+        d[qo + i] = q;
+        d[qo + sl - 1 - i] = p;
       }
-      if (LUT && (L & 1u) && gl == 0) d[a + half] = lut[d[a + half]];
+      if (LUT && (sl & 1u) && gl == 0) d[so + half] = lut[d[so + half]];
     } else if (LUT) {
-      for (u32 i = gl; i < L; i += G) d[a + i] = lut[d[a + i]];
+      for (u32 i = gl; i < sl; i += G) d[so + i] = lut[d[so + i]];
     }
     __syncwarp();
   }
 }
 
-// transform of all owned records of a tile, G lanes per record
-template <u32 G, u32 WPL>
-__device__ __forceinline__ void transform_tile(fq::Smem &sm, u8 *d, u32 n_own, int reverse, int use_lut) {
+// transform of all owned records of a tile, G lanes per record (r_line holds them in any order)
+template <class C, u32 G, u32 WPL>
+__device__ __forceinline__ void transform_tile(typename C::Smem &sm, u8 *d, u32 n_own, int reverse, int use_lut) {
   const u32 g = threadIdx.x / G, gl = threadIdx.x % G;
-  for (u32 rb = 0; rb < n_own; rb += fq::NT / G) {  // uniform trip count per CTA
+  for (u32 rb = 0; rb < n_own; rb += C::NT / G) {  // uniform trip count per CTA
     const u32 r = rb + g;
     u32 so = 0, sl = 0, qo = 0;
     if (r < n_own) {
       const u32 k = sm.r_line[r];
-      so = sm.ls[k + 1];
-      sl = sm.ls[k + 2] - 1u - so;
-      qo = sm.ls[k + 3];
+      so = sm.ls[k + 1] & 0x7fffu;
+      sl = (sm.ls[k + 2] & 0x7fffu) - 1u - so;
+      qo = sm.ls[k + 3] & 0x7fffu;
     }
     if (reverse) {
-      if (use_lut) seg_inplace<true, true, G, WPL>(d, so, sl, sm.lut, gl);
-      else seg_inplace<true, false, G, WPL>(d, so, sl, sm.lut, gl);
-      seg_inplace<true, false, G, WPL>(d, qo, sl, sm.lut, gl);
+      if (use_lut) record_inplace<true, true, G, WPL>(d, so, sl, qo, sm.lut, gl);
+      else record_inplace<true, false, G, WPL>(d, so, sl, qo, sm.lut, gl);
     } else {
-      seg_inplace<false, true, G, WPL>(d, so, sl, sm.lut, gl);
+      record_inplace<false, true, G, WPL>(d, so, sl, qo, sm.lut, gl);
     }
   }
 }
 
-__global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs a) {
   using namespace fq;
+  constexpr u32 NT = C::NT, CPL = C::CPL, NWARP = C::NWARP, T = C::T, LITER = C::LITER;
+  typedef typename C::Smem Smem;
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -187,24 +218,20 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
   }
   __syncthreads();
 
-  // bulk load of the region of tile `tile` into stage s; returns nothing, bytes may be 0 (then no barrier phase)
-  auto issue = [&](u32 tile, u32 s) {
-    const long long r0 = (long long)tile * T - PRE;  // global position of stage byte 0
-    long long g0 = r0 < 0 ? 0 : r0;
-    long long g1 = (long long)tile * T + T + H;
-    if (g1 > (long long)n16) g1 = n16;
-    if (g1 > g0) {
-      const u32 bytes = (u32)(g1 - g0);
-      tma::mbar_expect_tx(&sm.full[s], bytes);
-      tma::bulk_load(&sm.in[s][(u32)(g0 - r0)], a.in + g0, bytes, &sm.full[s]);
-    }
-  };
-  auto has_bulk = [&](u32 tile) {
-    const long long r0 = (long long)tile * T - PRE;
-    long long g0 = r0 < 0 ? 0 : r0;
-    long long g1 = (long long)tile * T + T + H;
-    if (g1 > (long long)n16) g1 = n16;
+  // bulk load of the region of tile `tile` into stage s; bytes may be 0 (then there is no barrier phase).
+  // n < 4 GiB - 1 MiB (engine.h kMaxBlockBytes), so t0 + T + H does not wrap.
+  auto bulk_range = [&](u32 tile, u32 &g0, u32 &g1) {
+    const u32 t0 = tile * T;
+    g0 = tile ? t0 - PRE : 0u;
+    g1 = t0 + T + H < n16 ? t0 + T + H : n16;
     return g1 > g0;
+  };
+  auto issue = [&](u32 tile, u32 s) {
+    u32 g0, g1;
+    if (bulk_range(tile, g0, g1)) {
+      tma::mbar_expect_tx(&sm.full[s], g1 - g0);
+      tma::bulk_load(&sm.in[s][g0 + PRE - tile * T], a.in + g0, g1 - g0, &sm.full[s]);
+    }
   };
 
   if (tid == 0) {
@@ -218,7 +245,7 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
   for (u32 tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, it++) {
     const u32 s = it % NSTAGE;
     const u32 parity = (it / NSTAGE) & 1u;
-    if (tid == 0) {
+    if (tid == 0 && !a.issue_late) {
       const u32 tn = tile + (NSTAGE - 1) * gridDim.x;
       if (it > 0) tma::bulk_wait_read();  // the stage being refilled was the source of the previous tile's store
       if (tn < a.n_tiles) issue(tn, (it + NSTAGE - 1) % NSTAGE);
@@ -228,165 +255,198 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
     u8 *d = stage + PRE;  // region byte 0 == global byte t0
     const u32 lim = (n - t0 < T + H) ? n - t0 : T + H;  // valid bytes of the region
     const bool eof = (n - t0) <= T + H;
-    if (has_bulk(tile)) tma::mbar_wait(&sm.full[s], parity);
+    {
+      u32 g0, g1;
+      if (bulk_range(tile, g0, g1)) tma::mbar_wait(&sm.full[s], parity);
+    }
     // bytes the bulk copy did not bring: the look-behind of tile 0, the ragged tail of the file, padding
-    if (tile == 0 || (unsigned long long)t0 + T + H > n16) {
-      const long long r0 = (long long)t0 - PRE;
+    if (tile == 0 || t0 + T + H > n16) {
       for (u32 i = tid; i < PRE + T + H + 16; i += NT) {
-        const long long g = r0 + i;
-        if (g < 0 || g >= (long long)n16) stage[i] = (g >= 0 && g < (long long)n) ? a.in[g] : (u8)'\n';
+        const bool before = t0 + i < PRE;  // only tile 0
+        const u32 g = t0 + i - PRE;
+        if (before || g >= n16) stage[i] = (!before && g < n) ? a.in[g] : (u8)'\n';
       }
       __syncthreads();
     }
 
-    // ---- newline scan: lane owns CPL consecutive 16-byte chunks; the 0x80 flag bytes of a chunk are packed into a
-    // position-ordered 16-bit mask with four IDP.4A (flag byte * {1,2,4,8} summed = nibble << 7)
-    const u32 span = (warp * 32u + lane) * (CPL * 16u);
-    u32 mlo, mhi;
-    {
-      u32 m16[CPL];
+    // ---- newline scan -> line starts (bit 15 = the line opens a record), grammar check, owned-record list.
+    // The halo is scanned only as far as records usually reach (a.scan_halo); a tile whose last owned record
+    // ends beyond that repeats the scan over the whole halo.
+    u32 hs = a.scan_halo;
+    u32 n_lines = 0, n_own = 0;
+    bool bad = false;
+    bool own0 = false;            // first pass over the line list: this thread's line opens an owned record
+    u32 bal0 = 0, own_pos0 = 0;   //   ... the warp's ballot of that, and the record's start
+    for (;;) {  // uniform
+      const u32 slim = lim < T + hs ? lim : T + hs;  // bytes scanned
+      const u32 span = (warp * 32u + lane) * (CPL * 16u);
+      u32 mlo = 0, mhi = 0;
+      if (warp * (32u * CPL * 16u) < slim) {
+        // lane owns CPL consecutive 16-byte chunks; the 0x80 flag bytes of a chunk are packed into a position-
+        // ordered 16-bit mask with four IDP.4A (flag byte * {1,2,4,8} summed = nibble << 7)
+        u32 m16[CPL];
 #pragma unroll
-      for (u32 j = 0; j < CPL; j++) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(d + span + j * 16u);
-        u32 lo = __dp4a(nl_flags(v.x), 0x08040201u, 0u);
-        lo = __dp4a(nl_flags(v.y), 0x80402010u, lo);
-        u32 hi = __dp4a(nl_flags(v.z), 0x08040201u, 0u);
-        hi = __dp4a(nl_flags(v.w), 0x80402010u, hi);
-        m16[j] = (lo >> 7) | (hi << 1);
-      }
-      mlo = m16[0] | (m16[1] << 16);
-      mhi = m16[2];
-    }
-    if (span + CPL * 16u > lim) {  // bytes past the end of the file do not count
-      const u32 valid = lim > span ? lim - span : 0u;
-      if (valid < 32u) { mlo &= (1u << valid) - 1u; mhi = 0; }
-      else mhi &= (1u << (valid - 32u)) - 1u;
-    }
-    const u32 cnt = __popc(mlo) + __popc(mhi);
-    u32 inc = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const u32 y = __shfl_up_sync(0xffffffffu, inc, off);
-      if ((int)lane >= off) inc += y;
-    }
-    if (lane == 31) sm.wtot[warp] = inc;
-    if (tid == 0) sm.bad = 0;
-    __syncthreads();
-    u32 base, n_nl;
-    {
-      u32 x = sm.wtot[lane & (NWARP - 1u)];
-#pragma unroll
-      for (int off = 1; off < (int)NWARP; off <<= 1) {
-        const u32 y = __shfl_up_sync(0xffffffffu, x, off, NWARP);
-        if ((int)(lane & (NWARP - 1u)) >= off) x += y;
-      }
-      n_nl = __shfl_sync(0xffffffffu, x, NWARP - 1u);
-      base = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
-      if (warp == 0) base = 0;
-    }
-    const bool virt = eof && lim > 0 && d[lim - 1] != '\n';  // unterminated last line
-    const bool overflow = n_nl + 2 > LCAP;
-    if (!overflow) {
-      u32 k = base + inc - cnt + 1;  // ls[k] = start of the line after the (k-1)-th newline
-      while (mlo) {
-        const u32 t = (u32)__ffs((int)mlo) - 1u;
-        mlo &= mlo - 1u;
-        sm.ls[k++] = (u16)(span + t + 1u);
-      }
-      while (mhi) {
-        const u32 t = (u32)__ffs((int)mhi) - 1u;
-        mhi &= mhi - 1u;
-        sm.ls[k++] = (u16)(span + 32u + t + 1u);
-      }
-      if (tid == 0) {
-        sm.ls[0] = 0;
-        if (virt) sm.ls[n_nl + 1] = (u16)(lim + 1);
-      }
-    }
-    if (virt) n_nl++;
-    __syncthreads();
-    if (overflow) {
-      if (tid == 0) atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
-      continue;  // uniform
-    }
-
-    // ---- record starts: line k (k <= n_nl) opens a record iff it starts with '@' and the line before is not a bare "+"
-    // whose own predecessor ended ... (rule pinned in SURVEY C.1: '\n@' unless preceded by "\n+")
-    for (u32 k = tid; k <= n_nl; k += NT) {
-      const u32 p = sm.ls[k];
-      bool rs = p < lim && d[p] == '@';
-      if (rs && k == 0) rs = (tile == 0) || d[-1] == '\n';
-      if (rs && (unsigned long long)t0 + p >= 3ull && d[(int)p - 3] == '\n' && d[(int)p - 2] == '+' && !(k == 0 && tile == 0))
-        rs = false;
-      sm.isrs[k] = rs ? 1 : 0;
-    }
-    __syncthreads();
-
-    // ---- owned records (start inside the tile), grammar check, ordered compaction
-    u32 run = 0;
-    for (u32 kb = 0; kb <= n_nl; kb += NT) {  // uniform trip count
-      const u32 k = kb + tid;
-      bool own = false;
-      if (k <= n_nl && sm.isrs[k] && sm.ls[k] < T) {
-        own = true;
-        bool ok = k + 4 <= n_nl;  // the four newlines of the record are inside the region
-        if (ok) {
-          const u32 l1 = sm.ls[k + 1], l2 = sm.ls[k + 2], l3 = sm.ls[k + 3], l4 = sm.ls[k + 4];
-          const u32 sl = l2 - 1 - l1, ql = l4 - 1 - l3;
-          ok = !sm.isrs[k + 1] && !sm.isrs[k + 2] && !sm.isrs[k + 3];
-          ok = ok && (l3 - l2 == 2) && d[l2] == '+';         // bare "+" line
-          ok = ok && sl == ql && !(sl > 0 && d[l1] == '+');  // a sequence line starting with '+' flips the parser
-          ok = ok && (sm.isrs[k + 4] || (eof && l4 >= lim)); // next line opens a record, or the file ends here
+        for (u32 j = 0; j < CPL; j++) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(d + span + j * 16u);
+          u32 lo = __dp4a(nl_flags(v.x), 0x08040201u, 0u);
+          lo = __dp4a(nl_flags(v.y), 0x80402010u, lo);
+          u32 hi = __dp4a(nl_flags(v.z), 0x08040201u, 0u);
+          hi = __dp4a(nl_flags(v.w), 0x80402010u, hi);
+          m16[j] = (lo >> 7) | (hi << 1);
         }
-        if (!ok) sm.bad = 1;
+        static_assert(CPL == 3 || CPL == 4, "mask packing");
+        mlo = m16[0] | (m16[1] << 16);
+        mhi = m16[2];
+        if (CPL == 4) mhi |= m16[CPL - 1] << 16;
+        if (span + CPL * 16u > slim) {  // bytes past the scanned range (or the end of the file) do not count
+          const u32 valid = slim > span ? slim - span : 0u;
+          if (valid < 32u) { mlo &= (1u << valid) - 1u; mhi = 0; }
+          else if (valid < CPL * 16u) mhi &= (1u << (valid - 32u)) - 1u;
+        }
       }
-      const u32 bal = __ballot_sync(0xffffffffu, own);
-      if (lane == 0) sm.wtot2[warp] = __popc(bal);
+      const u32 cnt = __popc(mlo) + __popc(mhi);
+      u32 inc = cnt;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, inc, off);
+        if ((int)lane >= off) inc += y;
+      }
+      if (lane == 31) sm.wtot[warp] = inc;
+      if (tid == 0) { sm.bad = 0; sm.rescan = 0; sm.n_list = 0; sm.kmin = 0xffffffffu; sm.kmax = 0; }
       __syncthreads();
-      u32 wb, tot;
+      u32 base, n_nl;
       {
-        u32 x = sm.wtot2[lane & (NWARP - 1u)];
+        u32 x = sm.wtot[lane & (NWARP - 1u)];
 #pragma unroll
         for (int off = 1; off < (int)NWARP; off <<= 1) {
           const u32 y = __shfl_up_sync(0xffffffffu, x, off, NWARP);
           if ((int)(lane & (NWARP - 1u)) >= off) x += y;
         }
-        tot = __shfl_sync(0xffffffffu, x, NWARP - 1u);
-        wb = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
-        if (warp == 0) wb = 0;
+        n_nl = __shfl_sync(0xffffffffu, x, NWARP - 1u);
+        base = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
+        if (warp == 0) base = 0;
       }
-      if (own) {
-        const u32 r = run + wb + __popc(bal & ((1u << lane) - 1u));
-        if (r < RCAP) sm.r_line[r] = (u16)k;
+      const bool virt = eof && slim == lim && lim > 0 && d[lim - 1] != '\n';  // unterminated last line
+      if (n_nl + 2 > LCAP) { bad = true; break; }
+      {
+        // record-start rule: a line opens a record iff it starts with '@' unless the line before it
+        // is a bare "+" ("\n+\n@" is the quality line of a record)
+        u32 k = base + inc - cnt + 1;  // ls[k] = start of the line after the (k-1)-th newline
+        while (mlo | mhi) {
+          u32 t;
+          if (mlo) { t = (u32)__ffs((int)mlo) - 1u; mlo &= mlo - 1u; }
+          else { t = 32u + (u32)__ffs((int)mhi) - 1u; mhi &= mhi - 1u; }
+          const u32 p = span + t + 1u;
+          u32 rs = 0;
+          if (p < lim && d[p] == '@') rs = (t0 + p >= 3u && d[(int)p - 3] == '\n' && d[(int)p - 2] == '+') ? 0u : 0x8000u;
+          sm.ls[k++] = (u16)(p | rs);
+        }
+        if (tid == 0) {
+          u32 rs0 = 0;
+          if (lim > 0 && d[0] == '@') {
+            if (tile == 0) rs0 = 0x8000u;
+            else if (d[-1] == '\n' && !(d[-3] == '\n' && d[-2] == '+')) rs0 = 0x8000u;
+          }
+          sm.ls[0] = (u16)rs0;
+          if (virt) sm.ls[n_nl + 1] = (u16)(lim + 1);
+        }
       }
-      run += tot;
+      n_lines = n_nl + (virt ? 1u : 0u);  // ls[0 .. n_lines] are valid
       __syncthreads();
+
+      // owned records = record lines that start inside the tile; each must be "@h \n s \n + \n q \n" with |s| == |q|
+      for (u32 kb = 0; kb <= n_lines; kb += NT) {  // uniform trip count
+        const u32 k = kb + tid;
+        bool own = false;
+        if (k <= n_lines) {
+          const u32 e0 = sm.ls[k];
+          if ((e0 & 0x8000u) && (e0 & 0x7fffu) < T) {
+            own = true;
+            if (kb == 0) own_pos0 = e0 & 0x7fffu;
+            if (k + 4 <= n_lines) {
+              const u32 e1 = sm.ls[k + 1], e2 = sm.ls[k + 2], e3 = sm.ls[k + 3], e4 = sm.ls[k + 4];
+              const u32 l1 = e1 & 0x7fffu, l2 = e2 & 0x7fffu, l3 = e3 & 0x7fffu, l4 = e4 & 0x7fffu;
+              const u32 sl = l2 - 1 - l1, ql = l4 - 1 - l3;
+              bool ok = ((e1 | e2 | e3) & 0x8000u) == 0;
+              ok = ok && (l3 - l2 == 2) && d[l2] == '+';         // bare "+" line
+              ok = ok && sl == ql && !(sl > 0 && d[l1] == '+');  // a sequence line starting with '+' flips the parser
+              ok = ok && ((e4 & 0x8000u) || (eof && l4 >= lim)); // next line opens a record, or the file ends here
+              if (!ok) sm.bad = 1;
+            } else if (slim < lim) {
+              sm.rescan = 1;  // the record ends beyond the scanned part of the halo
+            } else {
+              sm.bad = 1;     // longer than the halo, or truncated
+            }
+          }
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, own);
+        if (kb == 0) { own0 = own; bal0 = bal; }
+        u32 wpos = 0;
+        if (lane == 0) {
+          const u32 c = (u32)__popc(bal);
+          if (kb / NT < LITER) sm.wtot2[kb / NT][warp] = c;
+          if (c) {
+            wpos = atomicAdd(&sm.n_list, c);
+            atomicMin(&sm.kmin, kb + warp * 32u + (u32)__ffs((int)bal) - 1u);   // lines of the first / last owned record
+            atomicMax(&sm.kmax, kb + warp * 32u + 31u - (u32)__clz((int)bal));
+          }
+        }
+        wpos = __shfl_sync(0xffffffffu, wpos, 0);
+        if (own) {
+          const u32 r = wpos + (u32)__popc(bal & ((1u << lane) - 1u));
+          if (r < RCAP) sm.r_line[r] = (u16)k;
+        }
+      }
+      __syncthreads();
+      n_own = sm.n_list;
+      bad = sm.bad != 0 || n_own > RCAP;
+      if (tile == 0 && !(sm.ls[0] & 0x8000u)) bad = true;  // the file must open with a marked record
+      const bool rescan = sm.rescan != 0;
+      if (bad || !rescan || hs >= H) {
+        if (rescan) bad = true;
+        break;
+      }
+      hs = H;
+      __syncthreads();  // everybody has read the flags before thread 0 clears them again
     }
-    const u32 n_own = run;
-    bool bad = sm.bad != 0 || n_own > RCAP;
-    if (tile == 0 && !sm.isrs[0]) bad = true;  // the file must open with a marked record
+    // refill the stage the PREVIOUS tile was stored from (its bulk store has long finished reading by now)
+    if (tid == 0 && a.issue_late) {
+      const u32 tn = tile + (NSTAGE - 1) * gridDim.x;
+      if (it > 0) tma::bulk_wait_read();
+      if (tn < a.n_tiles) issue(tn, (it + NSTAGE - 1) % NSTAGE);
+    }
     if (bad) {
-      if (tid == 0) atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
+      if (tid == 0) {
+        atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
+        // diagnostics: first tile outside the grammar and what the CTA saw there
+        const unsigned long long info = ((unsigned long long)tile << 32) | ((u64)(sm.bad & 1u) << 31) | ((u64)(sm.rescan & 1u) << 30) |
+                                        ((u64)(n_own & 0x3ffu) << 16) | (n_lines & 0xffffu);
+        atomicMin((unsigned long long *)&a.st->counters[4], info);
+      }
       __syncthreads();
-      continue;
+      continue;  // uniform
     }
 
-    // ---- element slots + in-place transform
-    for (u32 r = tid; r < n_own; r += NT) a.slots[(size_t)tile * RCAP + r] = sm.ls[sm.r_line[r]];
-    if (tid == 0) a.tile_cnt[tile] = n_own;
+    // ---- in-place transform
     if (a.reverse || a.use_lut) {
-      if (a.group == 8) transform_tile<8, 8>(sm, d, n_own, a.reverse, a.use_lut);
-      else if (a.group == 16) transform_tile<16, 4>(sm, d, n_own, a.reverse, a.use_lut);
-      else transform_tile<32, 4>(sm, d, n_own, a.reverse, a.use_lut);
+      if (a.group == 8) {
+        if (a.wpl <= 5) transform_tile<C, 8, 5>(sm, d, n_own, a.reverse, a.use_lut);
+        else transform_tile<C, 8, 8>(sm, d, n_own, a.reverse, a.use_lut);
+      } else if (a.group == 16) {
+        transform_tile<C, 16, 4>(sm, d, n_own, a.reverse, a.use_lut);
+      } else {
+        transform_tile<C, 32, 4>(sm, d, n_own, a.reverse, a.use_lut);
+      }
     }
     tma::fence_proxy_async();
     __syncthreads();
 
-    // ---- owned byte range [lo, hi) -> out, same offsets: bulk store of the aligned body, ragged ends by warp 0
+    // ---- owned byte range [lo, hi) -> out, same offsets: bulk store of the aligned body, ragged ends by warp 0.
+    // Owned records are contiguous: from the first owned record line to the line after the last one.
     if (warp == 0 && n_own > 0) {
-      const u32 lo = sm.ls[sm.r_line[0]];
-      const u32 kl = sm.r_line[n_own - 1];
-      const u32 hi = sm.ls[kl + 4];  // start of the next record == one past the '\n' that ends the last owned one
+      const u32 kmin = sm.kmin, kmax = sm.kmax;
+      const u32 lo = sm.ls[kmin] & 0x7fffu;
+      const u32 hi = sm.ls[kmax + 4] & 0x7fffu;  // start of the next record == one past the '\n' that ends the last owned one
       const u32 lo16 = (lo + 15u) & ~15u, hi16 = hi & ~15u;
       u8 *go = a.out + t0;
       if (hi16 > lo16) {
@@ -403,26 +463,79 @@ __global__ void __launch_bounds__(fq::NT, 2) k_fastq_inplace(FqInplaceArgs a) {
       }
       if (eof && lane == 0 && hi >= lim) a.st->counters[1] = (u64)t0 + hi;  // total output bytes (n, or n + 1)
     }
-    // no barrier here: warp 0 reaches the next tile's barriers only after it has read what it needs
+
+    // ---- element slots in input order: rank of a record = owned records on earlier lines
+    if (n_lines < NT) {  // one pass over the line list (the usual case): ownership is still in registers
+      if (bal0) {
+        u32 wb = 0;
+        for (u32 w = 0; w < warp; w++) wb += sm.wtot2[0][w];
+        if (own0) a.slots[(size_t)tile * RCAP + wb + (u32)__popc(bal0 & ((1u << lane) - 1u))] = (u16)own_pos0;
+      }
+    } else {
+      u32 before = 0;  // owned records of earlier passes over the line list
+      for (u32 kb = 0; kb <= n_lines; kb += NT) {  // uniform trip count
+        const u32 it2 = kb / NT;
+        const u32 k = kb + tid;
+        bool own = false;
+        u32 e0 = 0;
+        if (k <= n_lines) {
+          e0 = sm.ls[k];
+          own = (e0 & 0x8000u) && (e0 & 0x7fffu) < T;
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, own);
+        u32 wb = 0, tot = 0;
+        if (it2 < LITER) {
+          for (u32 w = 0; w < NWARP; w++) {
+            const u32 c = sm.wtot2[it2][w];
+            if (w < warp) wb += c;
+            tot += c;
+          }
+        }
+        if (own) a.slots[(size_t)tile * RCAP + before + wb + (u32)__popc(bal & ((1u << lane) - 1u))] = (u16)(e0 & 0x7fffu);
+        before += tot;
+      }
+    }
+    if (tid == 0) a.tile_cnt[tile] = n_own;
+    // no barrier here: the next tile's first barrier comes before anything above is overwritten
   }
   if (tid == 0) tma::bulk_wait_all();
 }
 
 // element offsets from the per-tile slot lists: one warp per tile
 __global__ void k_fastq_elem_expand(const u32 *__restrict__ tile_cnt, const u64 *__restrict__ tile_base,
-                                    const u16 *__restrict__ slots, u64 *__restrict__ elem_off, u32 n_tiles) {
+                                    const u16 *__restrict__ slots, u64 *__restrict__ elem_off, u32 n_tiles, u32 tile_bytes) {
   const u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   const u32 c = tile_cnt[tile];
   const u64 b = tile_base[tile];
-  for (u32 r = lane; r < c; r += 32) elem_off[b + r] = (u64)tile * fq::T + slots[(size_t)tile * fq::RCAP + r];
+  for (u32 r = lane; r < c; r += 32) elem_off[b + r] = (u64)tile * tile_bytes + slots[(size_t)tile * fq::RCAP + r];
 }
 
-u32 fastq_inplace_tiles(u32 n) { return (n + fq::T - 1) / fq::T; }
+u32 fastq_inplace_tile_bytes(int variant) { return variant == 1 ? fq::CfgB::T : fq::CfgA::T; }
+u32 fastq_inplace_tiles(u32 n, int variant) {
+  const u32 t = fastq_inplace_tile_bytes(variant);
+  return (n + t - 1) / t;
+}
 u32 fastq_inplace_slot_stride() { return fq::RCAP; }
 
+template <class C>
+static void launch_fastq_inplace(FqInplaceArgs a, int n_sm, cudaStream_t s) {
+  const size_t smem = sizeof(typename C::Smem) + 16;
+#ifndef BSK_EMU
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_fastq_inplace<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+#endif
+  u32 grid = (u32)n_sm * C::CTAS;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid == 0) return;
+  BSK_LAUNCH(k_fastq_inplace<C>, grid, C::NT, smem, s, a);
+}
+
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
-                   int use_lut, int group, int n_sm, cudaStream_t s) {
+                   int use_lut, int group, u32 max_seg, u32 scan_halo, int variant, int n_sm, cudaStream_t s) {
   FqInplaceArgs a;
   a.in = in;
   a.n = n;
@@ -431,29 +544,24 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   a.tile_cnt = tile_cnt;
   a.slots = slots;
   a.st = st;
-  a.n_tiles = fastq_inplace_tiles(n);
+  a.n_tiles = fastq_inplace_tiles(n, variant);
   a.reverse = reverse;
   a.use_lut = use_lut;
   a.group = group;
-  const size_t smem = sizeof(fq::Smem) + 16;
-#ifndef BSK_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_fastq_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
-#endif
-  u32 grid = (u32)n_sm * 2u;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (grid == 0) return;
-  BSK_LAUNCH(k_fastq_inplace, grid, fq::NT, smem, s, a);
+  a.issue_late = getenv("BSK_FQ_EARLY") ? 0 : 1;
+  a.wpl = max_seg <= 157 ? 5 : 8;
+  scan_halo = (scan_halo + 15u) & ~15u;
+  a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > fq::H ? fq::H : scan_halo);
+  if (variant == 1) launch_fastq_inplace<fq::CfgB>(a, n_sm, s);
+  else launch_fastq_inplace<fq::CfgA>(a, n_sm, s);
 }
 
-void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles,
+void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
                        cudaStream_t s) {
   if (!n_tiles) return;
   const u64 threads = (u64)n_tiles * 32;
-  BSK_LAUNCH_FLAT(k_fastq_elem_expand, (u32)((threads + 255) / 256), 256, 0, s, tile_cnt, tile_base, slots, elem_off, n_tiles);
+  BSK_LAUNCH_FLAT(k_fastq_elem_expand, (u32)((threads + 255) / 256), 256, 0, s, tile_cnt, tile_base, slots, elem_off, n_tiles,
+                  fastq_inplace_tile_bytes(variant));
 }
 
 }  // namespace k

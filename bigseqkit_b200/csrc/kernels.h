@@ -98,11 +98,11 @@ void seq_fused(const u8 *in, u32 n, u8 *out, u64 *elem_off, const u8 *lut, void 
                EmitCfg cfg, int only_id, int fastq, int min_len, int max_len, cudaStream_t s);
 
 // ---- FASTQ same-layout in-place kernel (k_fastq_inplace.cu): TMA-staged, no inter-CTA dependency
-u32 fastq_inplace_tiles(u32 n);
+u32 fastq_inplace_tiles(u32 n, int variant);
 u32 fastq_inplace_slot_stride();
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
-                   int use_lut, int group, int n_sm, cudaStream_t s);
-void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles,
+                   int use_lut, int group, u32 max_seg, u32 scan_halo, int variant, int n_sm, cudaStream_t s);
+void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
                        cudaStream_t s);
 
 // ---- stats (k_stats.cu)

@@ -1,4 +1,5 @@
 // ops_fused.cu -- host side of the single-pass tile path (k_fused.cu) for `seq` on short records.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -101,6 +102,7 @@ int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) 
     }
   }
   first_seq_len_ = (u32)seq.size();
+  first_rec_bytes_ = end + 1;
   if (seq.size() > limit) seq.resize(limit);
   u8 cm[256];
   alphabet_class_masks(cm);
@@ -196,18 +198,23 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
     BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
     n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
   }
-  const u32 n_tiles = k::fastq_inplace_tiles(n);
+  int variant = 0;  // 0: 512-thread CTAs x 2 / SM, 20 KiB tiles; 1: 256-thread CTAs x 4 / SM, 12 KiB tiles
+  if (const char *e = getenv("BSK_FQ_VARIANT")) variant = atoi(e) == 0 ? 0 : 1;
+  const u32 n_tiles = k::fastq_inplace_tiles(n, variant);
   u8 *out = b_out_.get<u8>((size_t)n + 64);
   u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
   u16 *slots = b_slots_.get<u16>((size_t)n_tiles * k::fastq_inplace_slot_stride());
   BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
+  BSK_CUDA(cudaMemsetAsync(&d_status_->counters[4], 0xff, 8, stream));
   main_begin();
   // lanes per record: 8 lanes x 8 words hold segments up to ~256 B (reads), 32 x 4 up to ~512 B; longer ones take
   // the byte-pair path inside the kernel
   int group = first_seq_len_ <= 250 ? 8 : 32;
   if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : atoi(e) == 16 ? 16 : 32;
-  k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group, n_sm_,
-                   stream);
+  // the newline scan first covers the halo as far as two records like the first one reach
+  const u32 scan_halo = 2u * first_rec_bytes_ + 64u;
+  k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group,
+                   first_seq_len_, scan_halo, variant, n_sm_, stream);
   main_end();
   launches_++;
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
@@ -216,6 +223,12 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
   fetch_status();  // synchronises the stream
   if (h_status_->counters[0]) {
+    if (getenv("BSK_DEBUG")) {
+      const u64 info = h_status_->counters[4];
+      fprintf(stderr, "bsk: same-layout FASTQ kernel declined %llu tile(s); first: tile %u bad=%u rescan=%u n_own=%u n_lines=%u\n",
+              (unsigned long long)h_status_->counters[0], (unsigned)(info >> 32), (unsigned)((info >> 31) & 1),
+              (unsigned)((info >> 30) & 1), (unsigned)((info >> 16) & 0x3ff), (unsigned)(info & 0xffff));
+    }
     main_timed_ = false;
     timings.main_launches--;
     return kFusedFallback;
@@ -226,7 +239,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   u64 *elem = nullptr;
   if (want_elem_off) {
     elem = b_elem_.get<u64>((size_t)nrec + 2);
-    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, stream);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, stream);
     launches_++;
     memcpy(hs + 16, &total, 8);
     BSK_CUDA(cudaMemcpyAsync(elem + nrec, hs + 16, 8, cudaMemcpyHostToDevice, stream));

@@ -129,10 +129,12 @@ INPLACE_OPTS = [
 
 def inplace_inputs():
     return {
-        # 64-byte records: every 16 KiB / 20 KiB tile boundary is a record start
+        # 64-byte records: every 12 / 16 / 20 KiB tile boundary is a record start
         "rec64_tile_aligned": _fixed_fastq(2000, 8, 25, 21),
         # records of 1 KiB: tile boundaries fall at every phase of a record, starts on boundaries included
         "rec1024": _fixed_fastq(150, 10, 504, 22),
+        # 48-byte records: > 2000 lines per region, several passes of the CTA over the line list
+        "rec48_many_lines": _fixed_fastq(3000, 6, 18, 30),
         "reads150": synth.fastq_reads(400 << 10, seed=23).tobytes(),
         "iupac_lower": _fixed_fastq(700, 12, 151, 24, alphabet="ACGTNacgtnRYKMSWBDHVrykm"),
         "no_final_newline": synth.fastq_reads(90 << 10, seed=25).tobytes()[:-1],
@@ -140,6 +142,8 @@ def inplace_inputs():
         "len251_to_600": b"".join(_fixed_fastq(1, 20, 251 + 7 * i, 100 + i) for i in range(50)),  # byte-pair path
         "empty_seq_and_header": b"@\n\n+\n\n@a\nA\n+\nI\n" * 300,
         "qual_starts_with_at_and_plus": b"@r\nACGT\n+\n@+@+\n@s\nGG\n+\n+@\n" * 300,
+        # short first record (small first-attempt scan halo), then records that end far into the halo: rescan path
+        "short_then_long": _fixed_fastq(1, 4, 20, 27) + _fixed_fastq(120, 10, 900, 28) + _fixed_fastq(40, 10, 1700, 29),
         "tiny_file": b"@a\nACGT\n+\nIIII\n",
         "tiny_file_no_nl": b"@a\nAC\n+\nII",
     }
@@ -198,11 +202,14 @@ def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
     assert r.data == exp[0] and list(r.elem_off) == exp[1] and t["fused_blocks"] == 1
 
 
+@pytest.mark.parametrize("variant", ["0", "1"])
 @pytest.mark.parametrize("group", ["8", "16", "32"])
-def test_inplace_lane_group_variants(lib, monkeypatch, group):
+def test_inplace_lane_group_variants(lib, monkeypatch, group, variant):
     monkeypatch.setenv("BSK_FQ_GROUP", group)
+    monkeypatch.setenv("BSK_FQ_VARIANT", variant)
     opts = {"Reverse": True, "Complement": True}
-    for name in ("reads150", "len250", "len251_to_600", "rec64_tile_aligned", "empty_seq_and_header"):
+    for name in ("reads150", "len250", "len251_to_600", "rec64_tile_aligned", "empty_seq_and_header", "short_then_long",
+                 "no_final_newline", "rec48_many_lines"):
         data = inplace_inputs()[name]
         exp = oracle.seq(data, opts)
         r, t = run(lib, data, opts)

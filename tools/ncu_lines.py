@@ -26,7 +26,7 @@ for l in lines[start[0] + 1:]:
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         seq.append(cur)
 if len(seq) != len(ins):
     print("warning: %d sass rows vs %d disasm instructions" % (len(ins), len(seq)), file=sys.stderr)
@@ -52,6 +52,27 @@ def src(loc):
             src_cache[f] = []
     L = src_cache[f]
     return L[ln - 1].strip()[:100] if 0 < ln <= len(L) else ""
+# optional buckets: BUCKETS="name:lo-hi,name:lo-hi" over lines of the kernel's main file
+import os
+if os.environ.get("BUCKETS"):
+    bk = []
+    for part in os.environ["BUCKETS"].split(","):
+        nm, rg = part.split(":")
+        lo, hi = rg.split("-")
+        bk.append((nm, int(lo), int(hi)))
+    bt = {nm: [0, 0] for nm, _, _ in bk}
+    bt["other"] = [0, 0]
+    for loc, (n, smp) in agg.items():
+        nm = "other"
+        if loc and loc[0].startswith("k_"):
+            for b, lo, hi in bk:
+                if lo <= loc[1] <= hi:
+                    nm = b
+                    break
+        bt[nm][0] += n
+        bt[nm][1] += smp
+    for nm, (n, smp) in bt.items():
+        print("BUCKET %-14s %5.1f%% inst  %5.1f%% samples" % (nm, 100.0 * n / tot, 100.0 * smp / max(tots, 1)))
 for loc, (n, smp) in sorted(agg.items(), key=lambda kv: (kv[0] or ("", 0))):
     if 100.0 * n / tot >= min_pct or 100.0 * smp / max(tots, 1) >= min_pct:
         print("%5.1f%% inst %5.1f%% smp  %s:%s  %s" % (100.0 * n / tot, 100.0 * smp / max(tots, 1), loc[0] if loc else "?", loc[1] if loc else "?", src(loc)))
