@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-mib", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-block-mib", type=int, default=0, help="pipeline block of bsk_run_buffer (0 = library default, 64 MiB)")
     return ap.parse_args()
 
 
@@ -106,6 +107,40 @@ class ClockSampler(threading.Thread):
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def pcie_probe(torch, dev, mib=256, reps=4):
+    """pinned-memory DMA rates on this box: H2D alone, D2H alone, and both directions at once (GB/s per direction).
+    The end-to-end path moves every input byte H2D and every output byte D2H, so the last figure is its roofline."""
+    n = mib << 20
+    h_a = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_b = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return n * reps / (time.perf_counter() - t0) / 1e9
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    return {"h2d_gbs": timed(h2d), "d2h_gbs": timed(d2h), "bidir_gbs_per_direction": timed(both)}
 
 
 def main_reference(args):
@@ -209,8 +244,11 @@ def main_ours(args):
 
     # ---- e2e: pinned host in, pinned host out, through bsk_run_buffer
     e2e = None
+    pcie = None
     if not args.no_e2e:
-        os.environ.setdefault("BSK_BLOCK_BYTES", str(min(block_bytes, 1 << 30)))
+        pcie = pcie_probe(torch, dev) if rank == 0 else None
+        if args.e2e_block_mib:
+            os.environ["BSK_BLOCK_BYTES"] = str(args.e2e_block_mib << 20)
         for _ in range(2):
             r = op.call((h_in.data_ptr(), n), copy=False)
         barrier()
@@ -259,10 +297,15 @@ def main_ours(args):
             "parity_checked": True,
         }
         if e2e:
+            e2e_gbs = bytes_all * args.steps / e2e_max / 1e9
+            if pcie:
+                pcie["frac_of_bidir"] = e2e_gbs / world / pcie["bidir_gbs_per_direction"]
+            line["pcie_roofline"] = pcie
             line["e2e"] = {"value": rec_all * args.steps / e2e_max, "unit": "records/s",
                            "gb_per_s": bytes_all * args.steps / e2e_max / 1e9,
                            "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": e2e["d2h"],
-                           "api": "bsk_run_buffer (pinned host in -> pinned host out, element offsets included)"}
+                           "api": "bsk_run_buffer (pinned host in -> pinned host out, element offsets included; H2D / kernels / D2H "
+                                  "pipelined over %s MiB record-aligned blocks on three streams)" % (args.e2e_block_mib or 64)}
         if not args.no_cpu_baseline and world == 1:
             sample = np.ascontiguousarray(aligned_prefix(host_np, min(args.cpu_sample_mib << 20, n)))
             threads = os.cpu_count() or 1

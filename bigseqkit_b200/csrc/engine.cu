@@ -37,6 +37,14 @@ Engine::~Engine() {
   if (d_status_) cudaFree(d_status_);
   if (h_status_) cudaFreeHost(h_status_);
   for (auto &e : ev_) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) {
+    if (ev_in_done_[i]) cudaEventDestroy(ev_in_done_[i]);
+    if (ev_in_free_[i]) cudaEventDestroy(ev_in_free_[i]);
+    if (ev_out_ready_[i]) cudaEventDestroy(ev_out_ready_[i]);
+    if (ev_out_free_[i]) cudaEventDestroy(ev_out_free_[i]);
+  }
+  if (s_in_) { cudaStreamSynchronize(s_in_); cudaStreamDestroy(s_in_); }
+  if (s_out_) { cudaStreamSynchronize(s_out_); cudaStreamDestroy(s_out_); }
   free_op_state();
   if (stream) cudaStreamDestroy(stream);
 }

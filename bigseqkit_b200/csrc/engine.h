@@ -88,6 +88,11 @@ class Engine {
   DevBuf b_tables_, b_lens_sorted_, b_rle_u_, b_rle_c_;
   DevBuf b_op1_, b_op2_, b_op3_, b_op4_, b_op5_, b_op6_, b_op7_, b_op8_;
   PinnedBuf h_out_, h_elem_, h_small_;
+  // bsk_run_buffer pipeline: second input / output buffer sets, copy streams, hand-over events
+  DevBuf b_in2_, b_out2_, b_elem2_;
+  cudaStream_t s_in_ = nullptr, s_out_ = nullptr;
+  cudaEvent_t ev_in_done_[2] = {nullptr, nullptr}, ev_in_free_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_out_ready_[2] = {nullptr, nullptr}, ev_out_free_[2] = {nullptr, nullptr};
   u64 launches_ = 0;
   cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, indexed, main0, main1, end
   bool main_timed_ = false;

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "engine.h"
 #include "prims.h"
@@ -432,12 +433,17 @@ long Engine::stats_render(const char *file, const char *format, char *buf, size_
 }
 
 // ------------------------------------------------------------------ host-buffer entry point
-// One Call() on a partition in host memory: cut it into record-aligned blocks of at most
-// BSK_BLOCK_BYTES (default 1 GiB), stage each block to HBM, run the operator, bring the result back.
+// One Call() on a partition in host memory: cut it into record-aligned blocks of at most BSK_BLOCK_BYTES
+// (default 64 MiB), and run them through a three-stream pipeline so that PCIe stays busy in both directions
+// while the kernels run:
+//   copy-in stream   H2D of block i+1 into the other input buffer
+//   ctx stream       kernels of block i
+//   copy-out stream  D2H of block i-1 (records + element offsets) from the other output buffer
+// With pinned host memory the copies are true DMA; the end-to-end rate is then bound by PCIe, not by the kernels.
 static size_t env_block_bytes() {
   const char *e = getenv("BSK_BLOCK_BYTES");
   size_t v = e ? strtoull(e, nullptr, 10) : 0;
-  if (v < 4096) v = 1ull << 30;
+  if (v < 4096) v = 64ull << 20;
   if (v > kMaxBlockBytes / 2) v = kMaxBlockBytes / 2;
   return v;
 }
@@ -452,6 +458,11 @@ static size_t next_record_start(const u8 *d, size_t n, size_t from, bool fq) {
   return n;
 }
 
+__global__ void k_add_u64(u64 *p, u64 n, u64 add) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += add;
+}
+
 int Engine::run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out) {
   memset(out, 0, sizeof *out);
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
@@ -460,44 +471,103 @@ int Engine::run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out) {
   alphabet_ = o_.alphabet;
   alphabet_known_ = false;
   first_block_ = true;
+  if (!s_in_) {
+    BSK_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
+    BSK_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      BSK_CUDA(cudaEventCreateWithFlags(&ev_in_done_[i], cudaEventDisableTiming));
+      BSK_CUDA(cudaEventCreateWithFlags(&ev_in_free_[i], cudaEventDisableTiming));
+      BSK_CUDA(cudaEventCreateWithFlags(&ev_out_ready_[i], cudaEventDisableTiming));
+      BSK_CUDA(cudaEventCreateWithFlags(&ev_out_free_[i], cudaEventDisableTiming));
+    }
+  }
+  // ---- record-aligned cut points
   const size_t blk = env_block_bytes();
   const bool fq = n > 0 && in[0] == '@';
-  size_t pos = 0, out_used = 0, elem_used = 0;
-  u64 n_rec_total = 0;
-  bool first = true;
-  while (first || pos < n) {
-    first = false;
+  std::vector<size_t> cut;
+  cut.push_back(0);
+  while (cut.back() < n) {
+    const size_t pos = cut.back();
     size_t end = n;
     if (n - pos > blk) {
       end = next_record_start(in, n, pos + blk, fq);
       if (end - pos >= kMaxBlockBytes) { err = "a single record exceeds the 4 GiB block limit"; return BSK_ERR_DATA; }
     }
-    const size_t bn = end - pos;
-    u8 *d_in = b_in_.get<u8>(bn + 64);
-    if (bn) BSK_CUDA(cudaMemcpyAsync(d_in, in + pos, bn, cudaMemcpyHostToDevice, stream));
+    cut.push_back(end);
+  }
+  if (cut.size() == 1) cut.push_back(0);  // empty partition: one empty block
+  const size_t nb = cut.size() - 1;
+  size_t max_block = 0;
+  for (size_t i = 0; i < nb; i++) max_block = std::max(max_block, cut[i + 1] - cut[i]);
+  u8 *d_in[2] = {b_in_.get<u8>(max_block + 64), nb > 1 ? b_in2_.get<u8>(max_block + 64) : nullptr};
+  // outputs rarely exceed the input by much; growing later costs a pipeline drain
+  h_out_.reserve(n + n / 16 + 4096, false, 0);
+  if (want_elem_off) h_elem_.reserve(4096, false, 0);
+
+  auto upload = [&](size_t i) {
+    const size_t bn = cut[i + 1] - cut[i];
+    if (i >= 2) BSK_CUDA(cudaStreamWaitEvent(s_in_, ev_in_free_[i & 1], 0));  // kernels of block i-2 are done with it
+    if (bn) BSK_CUDA(cudaMemcpyAsync(d_in[i & 1], in + cut[i], bn, cudaMemcpyHostToDevice, s_in_));
+    BSK_CUDA(cudaEventRecord(ev_in_done_[i & 1], s_in_));
+  };
+
+  size_t out_used = 0, elem_used = 0;
+  u64 n_rec_total = 0;
+  bool out_busy[2] = {false, false};  // an asynchronous D2H still reads output buffer set b
+  int ob = 0;                         // output buffer set the next block writes
+  upload(0);
+  for (size_t i = 0; i < nb; i++) {
+    if (i + 1 < nb) upload(i + 1);
+    const size_t bn = cut[i + 1] - cut[i];
+    BSK_CUDA(cudaStreamWaitEvent(stream, ev_in_done_[i & 1], 0));
+    if (out_busy[ob]) BSK_CUDA(cudaStreamWaitEvent(stream, ev_out_free_[ob], 0));
     BlockOut bo;
-    int rc = process_block(d_in, (u32)bn, pid, bo);
-    if (rc != BSK_OK) return rc;
+    int rc = process_block(d_in[i & 1], (u32)bn, pid, bo);  // synchronises the ctx stream
+    if (rc != BSK_OK) {
+      cudaStreamSynchronize(s_in_);
+      cudaStreamSynchronize(s_out_);
+      return rc;
+    }
+    BSK_CUDA(cudaEventRecord(ev_in_free_[i & 1], stream));
     n_rec_total += bo.n_rec;
-    if (bo.n) {
+    // host arenas: growing them moves the data, so drain the copy-out stream first
+    if (out_used + bo.n + 64 > h_out_.cap) {
+      BSK_CUDA(cudaStreamSynchronize(s_out_));
       h_out_.reserve(out_used + bo.n + 64, true, out_used);
-      BSK_CUDA(cudaMemcpyAsync(h_out_.as<u8>() + out_used, bo.d_data, bo.n, cudaMemcpyDeviceToHost, stream));
     }
-    if (want_elem_off) {
+    if (want_elem_off && (elem_used + bo.n_elem + 2) * 8 > h_elem_.cap) {
+      BSK_CUDA(cudaStreamSynchronize(s_out_));
       h_elem_.reserve((elem_used + bo.n_elem + 2) * 8, true, elem_used * 8);
-      u64 *he = h_elem_.as<u64>() + elem_used;
-      if (bo.n_elem && bo.d_elem_off) {
-        BSK_CUDA(cudaMemcpyAsync(he, bo.d_elem_off, bo.n_elem * 8, cudaMemcpyDeviceToHost, stream));
-        BSK_CUDA(cudaStreamSynchronize(stream));
-        if (out_used)
-          for (u64 i = 0; i < bo.n_elem; i++) he[i] += out_used;
-      }
     }
-    BSK_CUDA(cudaStreamSynchronize(stream));
+    const bool want_elems = want_elem_off && bo.n_elem && bo.d_elem_off;
+    if (want_elems && out_used) {  // element offsets are relative to the block's output
+      BSK_LAUNCH_FLAT(k_add_u64, (u32)((bo.n_elem + 255) / 256), 256, 0, stream, bo.d_elem_off, (u64)bo.n_elem, (u64)out_used);
+      launches_++;
+    }
+    BSK_CUDA(cudaEventRecord(ev_out_ready_[ob], stream));
+    BSK_CUDA(cudaStreamWaitEvent(s_out_, ev_out_ready_[ob], 0));
+    if (bo.n) BSK_CUDA(cudaMemcpyAsync(h_out_.as<u8>() + out_used, bo.d_data, bo.n, cudaMemcpyDeviceToHost, s_out_));
+    if (want_elems)
+      BSK_CUDA(cudaMemcpyAsync(h_elem_.as<u64>() + elem_used, bo.d_elem_off, bo.n_elem * 8, cudaMemcpyDeviceToHost, s_out_));
+    BSK_CUDA(cudaEventRecord(ev_out_free_[ob], s_out_));
+    // the next block may only run ahead of this D2H if its results land in other buffers
+    const bool swappable = (bo.n == 0 || bo.d_data == b_out_.p) && (!want_elems || bo.d_elem_off == b_elem_.p);
+    if (swappable && i + 1 < nb) {
+      std::swap(b_out_.p, b_out2_.p);
+      std::swap(b_out_.cap, b_out2_.cap);
+      std::swap(b_elem_.p, b_elem2_.p);
+      std::swap(b_elem_.cap, b_elem2_.cap);
+      out_busy[ob] = true;
+      ob ^= 1;
+    } else {
+      BSK_CUDA(cudaStreamSynchronize(s_out_));
+      out_busy[ob] = false;
+    }
     out_used += bo.n;
     elem_used += bo.n_elem;
-    pos = end;
   }
+  BSK_CUDA(cudaStreamSynchronize(s_out_));
+  BSK_CUDA(cudaStreamSynchronize(s_in_));
   if (op_ == OP_GREP && o_.Count) {
     BlockOut bo;
     int rc = finish_grep_count(bo);

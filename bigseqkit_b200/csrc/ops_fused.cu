@@ -125,10 +125,7 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
     if (rc != BSK_OK) return rc;
     if (!ok) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; }
   } else {
-    u8 *hs = h_small_.as<u8>();
-    BSK_CUDA(cudaMemcpyAsync(hs, d_in, 1, cudaMemcpyDeviceToHost, stream));
-    BSK_CUDA(cudaStreamSynchronize(stream));
-    fastq = hs[0] == '@';
+    fastq = part_fastq_;  // every block of a partition starts on a record of the partition's format
   }
   EmitCfg cfg;
   bool need_lut = false;
