@@ -28,6 +28,8 @@ for l in lines[start[0] + 1:]:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         seq.append(cur)
+if len(ins) > len(seq) and len(ins) % len(seq) == 0:
+    ins = ins[:len(seq)]  # several launches in the report: attribute the first one
 if len(seq) != len(ins):
     print("warning: %d sass rows vs %d disasm instructions" % (len(ins), len(seq)), file=sys.stderr)
 agg = {}
