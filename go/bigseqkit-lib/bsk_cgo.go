@@ -1,0 +1,224 @@
+// Package main -- drop-in operators for the BigSeqKit executor plugin (bigseqkit.so) that run the per-record
+// hot path on a B200 through libbsk.so (include/bsk.h).  NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Go
+// toolchain, IgnisHPC absent): it is the binding a BigSeqKit maintainer adds next to bigseqkit-lib/*.go.
+//
+// The plugin keeps the reference's exported factories (bigseqkit-lib/seq.go:17-19 NewSeqTransform, stats.go
+// NewStats / NewStatsReduce, rmdup.go NewRmDupPrepare / NewRmDupCheck, translate.go NewTranslate, locate.go
+// NewLocate, grep.go NewGrep, subseq.go NewSubseqTransform), the same embedded base.I... types and the same
+// "opts" JSON variable (bigseqkit/helper.go:47-66), so IgnisHPC and the drivers (bigseqkit/, bigseqkit-py/,
+// bigseqkit-cli/) see an identical plugin.
+//
+// Build (inside ignishpc/go-compiler, with libbsk.so and bsk.h installed):
+//   CGO_CFLAGS="-I/opt/bsk/include" CGO_LDFLAGS="-L/opt/bsk/lib -lbsk" go build -buildmode=plugin -trimpath -o bigseqkit.so
+package main
+
+/*
+#include <stdlib.h>
+#include "bsk.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+
+	"ignis/executor/api"
+	"ignis/executor/api/base"
+	"ignis/executor/api/function"
+	"ignis/executor/api/iterator"
+)
+
+// bskOp is one operator instance between Before() and After(): one bsk_ctx per executor thread, because the
+// reference calls Call() concurrently, once per partition, from ctx.Threads() threads (bigseqkit-lib/helper.go:413-416).
+type bskOp struct {
+	name string
+	ctxs []*C.bsk_ctx
+}
+
+func (o *bskOp) before(context api.IContext, name string) error {
+	o.name = name
+	opts := C.CString(context.Vars()["opts"].(string)) // the reference's own JSON, defaults filled by the driver
+	defer C.free(unsafe.Pointer(opts))
+	cname := C.CString(name)
+	defer C.free(unsafe.Pointer(cname))
+	nGPU := int(C.bsk_device_count())
+	if nGPU < 1 {
+		return fmt.Errorf("bigseqkit-b200: no CUDA device visible to executor %d", context.ExecutorId())
+	}
+	dev := C.int(context.ExecutorId() % nGPU)
+	o.ctxs = make([]*C.bsk_ctx, context.Threads())
+	for i := range o.ctxs {
+		if rc := C.bsk_create(cname, opts, dev, &o.ctxs[i]); rc != C.BSK_OK {
+			return fmt.Errorf("%s", C.GoString(C.bsk_create_error())) // same text as the reference's Before()
+		}
+	}
+	return nil
+}
+
+func (o *bskOp) after() error {
+	for _, c := range o.ctxs {
+		C.bsk_destroy(c)
+	}
+	o.ctxs = nil
+	return nil
+}
+
+// call runs one partition: the iterator's record strings are packed into one pinned arena ('\n'-separated, exactly
+// the bytes PlainFile + ReadFixer produced), one bsk_run_buffer call does the work, and the returned arena is
+// sliced into Go strings by the element offsets.  One cgo call per partition, not per record.
+func (o *bskOp) call(pid int64, it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	ctx := o.ctxs[context.ThreadId()]
+	buf := make([]byte, 0, 64<<20)
+	for it.HasNext() {
+		e, err := it.Next()
+		if err != nil {
+			return nil, err
+		}
+		buf = append(buf, e...)
+		buf = append(buf, '\n')
+	}
+	var out C.bsk_out
+	var p *C.uint8_t
+	if len(buf) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&buf[0]))
+	}
+	if rc := C.bsk_run_buffer(ctx, p, C.size_t(len(buf)), C.int64_t(pid), &out); rc != C.BSK_OK {
+		return nil, fmt.Errorf("%s", C.GoString(C.bsk_last_error(ctx)))
+	}
+	n := int(out.n_elem)
+	res := make([]string, n)
+	if n > 0 {
+		data := unsafe.Slice((*byte)(unsafe.Pointer(out.data)), int(out.n))
+		off := unsafe.Slice((*uint64)(unsafe.Pointer(out.elem_off)), n+1)
+		for i := 0; i < n; i++ {
+			res[i] = string(data[off[i] : off[i+1]-1]) // element without the '\n' FileStore adds back
+		}
+	}
+	return res, nil
+}
+
+// ---- SeqTransform: bigseqkit-lib/seq.go:17-269
+func NewSeqTransform() any { return &SeqTransform{} }
+
+type SeqTransform struct {
+	base.IMapPartitions[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *SeqTransform) Before(context api.IContext) error { return t.op.before(context, "SeqTransform") }
+func (t *SeqTransform) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(0, it, context)
+}
+
+// ---- SubseqTransform (region mode): bigseqkit-lib/subseq.go:22-526
+func NewSubseqTransform() any { return &SubseqTransform{} }
+
+type SubseqTransform struct {
+	base.IMapPartitions[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *SubseqTransform) Before(context api.IContext) error { return t.op.before(context, "SubseqTransform") }
+func (t *SubseqTransform) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(0, it, context)
+}
+
+// ---- Translate: bigseqkit-lib/translate.go:21-145
+func NewTranslate() any { return &Translate{} }
+
+type Translate struct {
+	base.IMapPartitions[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *Translate) Before(context api.IContext) error { return t.op.before(context, "Translate") }
+func (t *Translate) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(0, it, context)
+}
+
+// ---- Locate / Grep: IMapPartitionsWithIndex (bigseqkit-lib/locate.go:19,195 ; grep.go:24,544)
+func NewLocate() any { return &Locate{} }
+
+type Locate struct {
+	base.IMapPartitionsWithIndex[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *Locate) Before(context api.IContext) error { return t.op.before(context, "Locate") }
+func (t *Locate) Call(pid int64, it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(pid, it, context) // header row only in partition 0 (locate.go:198-204)
+}
+
+func NewGrep() any { return &Grep{} }
+
+type Grep struct {
+	base.IMapPartitionsWithIndex[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *Grep) Before(context api.IContext) error { return t.op.before(context, "Grep") }
+func (t *Grep) Call(pid int64, it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(pid, it, context)
+}
+
+// ---- Stats / StatsReduce: bigseqkit-lib/stats.go:16-137.  The map value keeps the reference's encoding
+// (length -> count, sentinel keys -1 Q20, -2 Q30, -3 gap sum, -4 alphabet tag) so bigseqkit/stats.go:96-166 is unchanged.
+func NewStats() any { return &Stats{} }
+
+type Stats struct {
+	base.IMapPartitions[string, map[int64]int64]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *Stats) Before(context api.IContext) error { return t.op.before(context, "Stats") }
+func (t *Stats) Call(it iterator.IReadIterator[string], context api.IContext) ([]map[int64]int64, error) {
+	ctx := t.op.ctxs[context.ThreadId()]
+	C.bsk_reset(ctx)
+	if _, err := t.op.call(0, it, context); err != nil {
+		return nil, err
+	}
+	var s C.bsk_stats
+	if rc := C.bsk_stats_result(ctx, &s); rc != C.BSK_OK {
+		return nil, fmt.Errorf("%s", C.GoString(C.bsk_last_error(ctx)))
+	}
+	m := make(map[int64]int64, int(s.n_hist)+4)
+	lens := unsafe.Slice((*uint64)(unsafe.Pointer(s.hist_len)), int(s.n_hist))
+	cnts := unsafe.Slice((*uint64)(unsafe.Pointer(s.hist_cnt)), int(s.n_hist))
+	for i := range lens {
+		m[int64(lens[i])] = int64(cnts[i])
+	}
+	m[-1], m[-2], m[-3] = int64(s.q20), int64(s.q30), int64(s.sum_gap)
+	switch C.GoString(&s._type[0]) {
+	case "DNA":
+		m[-4] = 'D'
+	case "RNA":
+		m[-4] = 'R'
+	case "":
+		m[-4] = 'U'
+	default:
+		m[-4] = 'F'
+	}
+	return []map[int64]int64{m}, nil
+}
+
+// ---- RmDup: the reference's Prepare -> GroupByKey -> Check pipeline shuffles every record; the accelerated
+// operator removes duplicates inside a partition in one call ("RmDup"), and exposes the int64 keys
+// (bsk_rmdup_keys) for drivers that keep the GroupByKey exchange across partitions.
+func NewRmDupPrepare() any { return &RmDup{} }
+
+type RmDup struct {
+	base.IMapPartitions[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *RmDup) Before(context api.IContext) error { return t.op.before(context, "RmDup") }
+func (t *RmDup) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(0, it, context)
+}
