@@ -35,14 +35,13 @@ namespace k {
 namespace fq {
 constexpr u32 H = 4096;        // halo bytes (longest record the kernel accepts, roughly)
 constexpr u32 PRE = 16;        // look-behind bytes in front of the tile
-constexpr u32 NSTAGE = 3;
-constexpr u32 LCAP = 3072;     // line starts per region
 constexpr u32 RCAP = 512;      // owned records per tile (slot stride)
 
 // CTA shape: NT threads, every lane scans CPL consecutive 16-byte chunks, so tile + halo = NT * CPL * 16 bytes
-template <u32 NT_, u32 CPL_, u32 CTAS_>
+template <u32 NT_, u32 CPL_, u32 CTAS_, u32 NSTAGE_, u32 LCAP_ = 3072>
 struct Cfg {
-  static constexpr u32 NT = NT_, CPL = CPL_, CTAS = CTAS_;
+  static constexpr u32 NT = NT_, CPL = CPL_, CTAS = CTAS_, NSTAGE = NSTAGE_;
+  static constexpr u32 LCAP = LCAP_;                          // line starts per region
   static constexpr u32 NWARP = NT / 32;
   static constexpr u32 T = NT * CPL * 16 - H;                 // tile bytes
   static constexpr u32 STAGE = PRE + T + H + 16;
@@ -59,8 +58,12 @@ struct Cfg {
     u32 bad, rescan, n_list, kmin, kmax;
   };
 };
-typedef Cfg<512, 3, 2> CfgA;   // 20 KiB tiles, 2 CTAs / SM
-typedef Cfg<256, 4, 4> CfgB;   // 12 KiB tiles, 4 CTAs / SM: smaller barrier domains, more phase diversity per SM
+typedef Cfg<512, 3, 2, 3> CfgA;   // 20 KiB tiles, 2 CTAs / SM, 3-stage ring
+typedef Cfg<256, 4, 4, 3> CfgB;   // 12 KiB tiles, 4 CTAs / SM: smaller barrier domains (3 resident: shared memory)
+typedef Cfg<512, 3, 2, 4> CfgC;   // as A with a 4-stage ring (loads issued 2.6 tiles ahead)
+typedef Cfg<512, 3, 3, 2> CfgD;   // as A with a 2-stage ring and 3 CTAs / SM (<= 40 registers per thread)
+typedef Cfg<512, 3, 4, 2, 2048> CfgE;   // 4 CTAs / SM: 64 warps, <= 32 registers per thread, 55 KB of shared memory
+typedef Cfg<384, 4, 4, 2, 2048> CfgF;   // 4 CTAs / SM of 12 warps, <= 40 registers per thread
 }  // namespace fq
 
 struct FqInplaceArgs {
@@ -204,7 +207,7 @@ __device__ __forceinline__ void transform_tile(typename C::Smem &sm, u8 *d, u32 
 template <class C>
 __global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs a) {
   using namespace fq;
-  constexpr u32 NT = C::NT, CPL = C::CPL, NWARP = C::NWARP, T = C::T, LITER = C::LITER;
+  constexpr u32 NT = C::NT, CPL = C::CPL, NWARP = C::NWARP, T = C::T, LITER = C::LITER, NSTAGE = C::NSTAGE, LCAP = C::LCAP;
   typedef typename C::Smem Smem;
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
@@ -316,14 +319,15 @@ __global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs 
       __syncthreads();
       u32 base, n_nl;
       {
-        u32 x = sm.wtot[lane & (NWARP - 1u)];
+        static_assert(NWARP <= 16, "warp totals are scanned by 16 lanes");
+        u32 x = (lane & 15u) < NWARP ? sm.wtot[lane & 15u] : 0u;
 #pragma unroll
-        for (int off = 1; off < (int)NWARP; off <<= 1) {
-          const u32 y = __shfl_up_sync(0xffffffffu, x, off, NWARP);
-          if ((int)(lane & (NWARP - 1u)) >= off) x += y;
+        for (int off = 1; off < 16; off <<= 1) {
+          const u32 y = __shfl_up_sync(0xffffffffu, x, off, 16);
+          if ((int)(lane & 15u) >= off) x += y;
         }
-        n_nl = __shfl_sync(0xffffffffu, x, NWARP - 1u);
-        base = __shfl_sync(0xffffffffu, x, (warp + NWARP - 1u) & (NWARP - 1u));
+        n_nl = __shfl_sync(0xffffffffu, x, 15);
+        base = __shfl_sync(0xffffffffu, x, (warp + 15u) & 15u);
         if (warp == 0) base = 0;
       }
       const bool virt = eof && slim == lim && lim > 0 && d[lim - 1] != '\n';  // unterminated last line
@@ -358,6 +362,11 @@ __global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs 
       for (u32 kb = 0; kb <= n_lines; kb += NT) {  // uniform trip count
         const u32 k = kb + tid;
         bool own = false;
+        if (kb + warp * 32u > n_lines) {  // this warp's lines are past the end of the list (warp-uniform)
+          if (kb == 0) { own0 = false; bal0 = 0; }
+          if (lane == 0 && kb / NT < LITER) sm.wtot2[kb / NT][warp] = 0;
+          continue;
+        }
         if (k <= n_lines) {
           const u32 e0 = sm.ls[k];
           if ((e0 & 0x8000u) && (e0 & 0x7fffu) < T) {
@@ -511,7 +520,8 @@ __global__ void k_fastq_elem_expand(const u32 *__restrict__ tile_cnt, const u64 
   for (u32 r = lane; r < c; r += 32) elem_off[b + r] = (u64)tile * tile_bytes + slots[(size_t)tile * fq::RCAP + r];
 }
 
-u32 fastq_inplace_tile_bytes(int variant) { return variant == 1 ? fq::CfgB::T : fq::CfgA::T; }
+u32 fastq_inplace_tile_bytes(int variant) { return variant == 1 ? fq::CfgB::T : fq::CfgA::T; }  // all others share A's tile
+static_assert(fq::CfgC::T == fq::CfgA::T && fq::CfgD::T == fq::CfgA::T && fq::CfgE::T == fq::CfgA::T && fq::CfgF::T == fq::CfgA::T, "tile bytes");
 u32 fastq_inplace_tiles(u32 n, int variant) {
   const u32 t = fastq_inplace_tile_bytes(variant);
   return (n + t - 1) / t;
@@ -553,6 +563,10 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > fq::H ? fq::H : scan_halo);
   if (variant == 1) launch_fastq_inplace<fq::CfgB>(a, n_sm, s);
+  else if (variant == 2) launch_fastq_inplace<fq::CfgC>(a, n_sm, s);
+  else if (variant == 3) launch_fastq_inplace<fq::CfgD>(a, n_sm, s);
+  else if (variant == 4) launch_fastq_inplace<fq::CfgE>(a, n_sm, s);
+  else if (variant == 5) launch_fastq_inplace<fq::CfgF>(a, n_sm, s);
   else launch_fastq_inplace<fq::CfgA>(a, n_sm, s);
 }
 

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Device-resident timings of the other operators on the BASELINE.json config shapes (one JSON line per operator).
+Not the driver's bench (that is bench.py, configs[1]); these lines document stats / rmdup / translate / locate."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mib", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ops", default="stats_fasta,stats_fastq,rmdup,translate,locate")
+    ap.add_argument("--cpu", action="store_true", help="also time the oracle port on all host cores (seq/stats/rmdup)")
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import oracle
+    from bigseqkit_b200 import Operator, synth
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    nbytes = args.mib << 20
+    rng = np.random.Generator(np.random.PCG64(40))
+    panel = ["".join("ACGT"[i] for i in rng.integers(0, 4, 12)) for _ in range(1000)]
+    cases = {
+        "stats_fasta": ("Stats", {"Tabular": True}, lambda: synth.fasta_reads(nbytes // 114, read_len=100, seed=1), "stats", 1.0),
+        "stats_fastq": ("Stats", {"Tabular": True, "All": True}, lambda: synth.fastq_reads(nbytes, seed=2), "stats", 1.0),
+        "rmdup": ("RmDup", {"BySeq": True}, lambda: synth.fastq_reads(nbytes, seed=3, dup_frac=0.2), "rmdup", None),
+        "translate": ("Translate", {"Frame": ["6"]}, lambda: synth.fasta_cds(nbytes, seed=5), None, None),
+        "locate": ("Locate", {"Pattern": panel}, lambda: synth.fasta_contigs(min(nbytes, 256 << 20), seed=4), None, 1.0),
+    }
+    for name in args.ops.split(","):
+        opn, opts, gen, cpu_op, alg_factor = cases[name]
+        host = gen()
+        n = host.nbytes
+        d_in = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+        d_in[:n].copy_(torch.from_numpy(host))
+        torch.cuda.synchronize()
+        op = Operator(opn, opts, device=0)
+        ext = torch.cuda.ExternalStream(op.stream(), device=dev)
+        for _ in range(args.warmup):
+            op.reset()
+            out = op.call_device(d_in.data_ptr(), n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        launches = 0
+        e0.record(ext)
+        for _ in range(args.steps):
+            op.reset()
+            out = op.call_device(d_in.data_ptr(), n)
+            launches += op.timings()["kernel_launches"]
+        e1.record(ext)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        n_rec, n_out = int(out.n_records), int(out.n)
+        alg = n * alg_factor if alg_factor else n + n_out + (16 * n_rec if name == "rmdup" else 0)
+        line = {"op": name, "operator": opn, "opts": {k: (v if k != "Pattern" else "1000 x 12-mer") for k, v in opts.items()},
+                "in_bytes": n, "out_bytes": n_out, "records": n_rec, "ms_per_step": ms, "records_per_s": n_rec / ms * 1e3,
+                "gb_per_s": n / ms / 1e6, "algorithmic_bytes": alg, "whole_step_frac_of_hbm_peak": alg / ms / 1e6 / peak,
+                "gpu_launches_per_step": launches // args.steps, "fused_blocks": op.timings()["fused_blocks"]}
+        if args.cpu and cpu_op:
+            threads = os.cpu_count() or 1
+            sample = np.ascontiguousarray(host[: min(n, 256 << 20)])
+            k = sample.tobytes().rfind(b"\n@" if sample[0] == 0x40 else b"\n>")
+            sample = np.ascontiguousarray(sample[: k + 1])
+            t0 = time.perf_counter()
+            nr, _ = oracle.run_mt(cpu_op, sample.ctypes.data, sample.nbytes, opts, threads)
+            dt = time.perf_counter() - t0
+            line["cpu_port"] = {"records_per_s": nr / dt, "gb_per_s": sample.nbytes / dt / 1e9, "cores": threads}
+        print(json.dumps(line), flush=True)
+        op.close()
+        del d_in
+
+
+if __name__ == "__main__":
+    main()
