@@ -144,6 +144,7 @@ class Engine {
   int op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo);
   // same-layout FASTQ kernel (k_fastq_inplace.cu); kFusedFallback when the block is outside its grammar
   int op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg, const u8 *h_lut, bool need_lut, BlockOut &bo);
+  int op_stats_tile(const u8 *d_in, u32 n, BlockOut &bo);
   int n_sm_ = 0;
   u32 first_rec_bytes_ = 0;
   u32 first_seq_len_ = 0;  // sequence length of the partition's first record (lane-group choice of the tile kernels)

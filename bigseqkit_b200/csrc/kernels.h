@@ -105,6 +105,11 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
 void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
                        cudaStream_t s);
 
+// ---- stats on short records in one streaming pass (k_stats_tile.cu)
+u32 stats_tile_bins();
+void stats_tile(const u8 *in, u32 n, u64 *hist, DevStatus *st, int fastq, int all, int fq_offset, const u8 *gap_letters,
+                int n_gap, u32 scan_halo, int n_sm, cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

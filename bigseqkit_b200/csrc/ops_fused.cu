@@ -186,6 +186,80 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
   return BSK_OK;
 }
 
+// `stats` on short records: one streaming kernel (k_stats_tile.cu), histogram + counters merged on the host.
+// bigseqkit-lib/stats.go:48-117; the totals keep sum semantics.
+int Engine::op_stats_tile(const u8 *d_in, u32 n, BlockOut &bo) {
+  if (n == 0 || !fused_ok_ || getenv("BSK_NO_STATS_TILE")) return kFusedFallback;
+  u8 gaps[4];
+  int n_gap = 0;
+  if (o_.All) {  // the kernel compares against up to four distinct gap letters
+    for (unsigned char c : o_.GapLetters) {
+      bool seen = false;
+      for (int i = 0; i < n_gap; i++) seen = seen || gaps[i] == c;
+      if (seen) continue;
+      if (n_gap == 4) return kFusedFallback;
+      gaps[n_gap++] = c;
+    }
+  }
+  bool fastq = false, ok = false;
+  const int saved_alpha = alphabet_;
+  const bool saved_known = alphabet_known_;
+  if (!alphabet_known_ || first_block_) {
+    int rc = first_record_alphabet(d_in, n, fastq, ok);
+    if (rc != BSK_OK) return rc;
+    if (!ok) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; }
+  } else {
+    fastq = part_fastq_;
+  }
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, device_ >= 0 ? device_ : 0));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  reset_status();
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  const u32 bins = k::stats_tile_bins();
+  u64 *d_hist = b_op1_.get<u64>(bins);
+  BSK_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)bins * 8, stream));
+  main_begin();
+  k::stats_tile(d_in, n, d_hist, d_status_, fastq ? 1 : 0, o_.All ? 1 : 0, o_.fq_offset, gaps, n_gap,
+                2u * first_rec_bytes_ + 64u, n_sm_, stream);
+  main_end();
+  launches_++;
+  h_probe_.reserve((size_t)bins * 8 + 16);
+  u64 *h_hist = h_probe_.as<u64>();
+  BSK_CUDA(cudaMemcpyAsync(h_hist, d_hist, (size_t)bins * 8, cudaMemcpyDeviceToHost, stream));
+  fetch_status();  // synchronises the stream
+  if (h_status_->counters[0]) {
+    alphabet_ = saved_alpha;
+    alphabet_known_ = saved_known;
+    main_timed_ = false;
+    timings.main_launches--;
+    return kFusedFallback;
+  }
+  for (u32 i = 0; i < bins; i++)
+    if (h_hist[i]) hist_[i] += h_hist[i];
+  if (o_.All) {
+    q20_ += h_status_->counters[1];
+    q30_ += h_status_->counters[2];
+    gap_ += h_status_->counters[3];
+  }
+  const u64 nrec = h_status_->counters[5];
+  if (!stats_type_set_) {  // stats.go:106-114 + bigseqkit/stats.go:109-130
+    if (alphabet_ == AB_DNARED) stats_type_ = "DNA";
+    else if (alphabet_ == AB_RNARED) stats_type_ = "RNA";
+    else stats_type_ = alphabet_name(first_guess_);
+    stats_type_set_ = true;
+  }
+  fastq_ = fastq;
+  if (first_block_) part_fastq_ = fastq;
+  n_rec_ = (u32)nrec;
+  bo.n_rec = nrec;
+  if (nrec) any_record_ = true;
+  timings.fused_blocks++;
+  return BSK_OK;
+}
+
 // `seq` on FASTQ in same-layout mode: one streaming kernel + the element-offset expansion.
 int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg, const u8 *h_lut, bool need_lut, BlockOut &bo) {
   (void)h_lut;

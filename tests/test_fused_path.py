@@ -113,6 +113,8 @@ def _fixed_fastq(n_rec, hdr_len, seq_len, seed, alphabet="ACGTN", plus=""):
         h = ("%0*d" % (hdr_len, i))[-hdr_len:] if hdr_len else ""
         s = "".join(rng.choice(alphabet) for _ in range(seq_len))
         q = "".join(chr(rng.randint(33, 74)) for _ in range(seq_len))
+        if plus and q[:1] == "@":
+            q = "I" + q[1:]  # "\n@" after a "+name" line would be framed as a record start
         out.append("@%s\n%s\n+%s\n%s\n" % (h, s, plus, q))
     return "".join(out).encode()
 
