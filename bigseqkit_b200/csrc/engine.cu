@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "prims.h"
@@ -274,14 +275,32 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
     prim::select_flagged_u64(ooff, keep, elem, d_nsel, n_rec_, b_tmp_, stream);
     BSK_CUDA(cudaMemcpyAsync(hs + 8, d_nsel, 4, cudaMemcpyDeviceToHost, stream));
   }
+  // records printed exactly as they stand in the input (rmdup, grep, filters on single-line records) are compacted
+  // as byte ranges instead of being re-formatted byte by byte
+  const bool try_contig = !squeezed_ && n_rec_ && cfg.marker && cfg.print_name && cfg.print_seq && !cfg.reverse && !lut &&
+                          views_.seqb == in_ && (fastq_ ? (cfg.print_qual && cfg.plus_line && views_.qualb == in_) : !cfg.print_qual) &&
+                          getenv("BSK_NO_CONTIG") == nullptr;
+  if (try_contig) {
+    BSK_CUDA(cudaMemsetAsync(&d_status_->counters[7], 0, 8, stream));
+    k::contig_check(views_, cfg, keep, fastq_ ? 1 : 0, n_, &d_status_->counters[7], stream);
+    launches_++;
+    BSK_CUDA(cudaMemcpyAsync(hs + 16, &d_status_->counters[7], 8, cudaMemcpyDeviceToHost, stream));
+  }
   BSK_CUDA(cudaStreamSynchronize(stream));
   u64 total;
   memcpy(&total, hs, 8);
   u32 nsel = n_rec_;
   if (keep) memcpy(&nsel, hs + 8, 4);
+  u64 not_contig = 1;
+  if (try_contig) memcpy(&not_contig, hs + 16, 8);
   u8 *out = b_out_.get<u8>((size_t)total + 64);
   main_begin();
-  k::emit(views_, cfg, ooff, out, total, lut, stream);
+  if (not_contig == 0) {
+    k::emit_contig(views_, ooff, out, total, n_, stream);
+    if (total) BSK_CUDA(cudaMemsetAsync(out + total - 1, '\n', 1, stream));  // input without a final newline
+  } else {
+    k::emit(views_, cfg, ooff, out, total, lut, stream);
+  }
   main_end();
   launches_++;
   bo.d_data = out;

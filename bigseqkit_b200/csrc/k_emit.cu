@@ -77,38 +77,159 @@ __device__ __forceinline__ u8 rec_byte(const RecViews &v, const EmitCfg &c, cons
   return '\n';
 }
 
-__global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
-                                              u64 total, const u8 *__restrict__ lut) {
-  const u64 o = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
-  if (o >= total) return;
-  u32 lo = 0, hi = v.n_rec;  // off[lo] <= o < off[hi]
+// last record r in [0, n_rec) with off[r] <= o, found by a whole warp: 32 probes per step instead of one
+__device__ __forceinline__ u32 warp_search(const u64 *__restrict__ off, u32 n_rec, u64 o) {
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n_rec;  // off[lo] <= o ; hi == n_rec or off[hi] > o
+  while (hi - lo > 1) {
+    const u32 span = hi - lo;
+    const u32 step = (span + 32) / 33;
+    const u32 idx = lo + (lane + 1) * step;
+    const bool le = idx < hi && off[idx] <= o;
+    const u32 cnt = (u32)__popc(__ballot_sync(0xffffffffu, le));  // off[] is monotone: the true lanes are a prefix
+    const u32 nlo = lo + cnt * step;
+    const u32 nhi = lo + (cnt + 1) * step;
+    lo = nlo;
+    if (nhi < hi) hi = nhi;
+  }
+  return lo;
+}
+
+static const u32 kEmitChunks = 4;  // 16-byte chunks per thread: a CTA of 256 threads writes 16 KiB
+
+// record range [r0, r1] that covers the CTA's output bytes, found once per CTA
+__device__ __forceinline__ void cta_record_range(const u64 *__restrict__ off, u32 n_rec, u64 o0, u64 total, u32 *s_r) {
+  const u32 warp = threadIdx.x >> 5;
+  if (warp < 2) {
+    u64 o = warp == 0 ? o0 : o0 + (u64)blockDim.x * 16ull * kEmitChunks - 1;
+    if (o >= total) o = total - 1;
+    const u32 r = warp_search(off, n_rec, o);
+    if ((threadIdx.x & 31) == 0) s_r[warp] = r;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ u32 search_in(const u64 *__restrict__ off, u32 lo, u32 hi, u64 o) {  // off[lo] <= o < off[hi]
   while (hi - lo > 1) {
     const u32 mid = lo + ((hi - lo) >> 1);
     if (off[mid] <= o) lo = mid;
     else hi = mid;
   }
-  u32 r = lo;
-  RecOut ro = load_rec(v, c, r);
-  u64 rend = off[r + 1];
-  u32 p = (u32)(o - off[r]);
-  u32 w[4] = {0, 0, 0, 0};
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
+                                              u64 total, const u8 *__restrict__ lut) {
+  __shared__ u32 s_r[2];
+  const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
+  cta_record_range(off, v.n_rec, o0, total, s_r);
+  for (u32 ch = 0; ch < kEmitChunks; ch++) {
+    const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
+    if (o >= total) return;
+    u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
+    RecOut ro = load_rec(v, c, r);
+    u64 rend = off[r + 1];
+    u32 p = (u32)(o - off[r]);
+    u32 w[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int b = 0; b < 16; b++) {
-    const u64 pos = o + (u64)b;
-    if (pos < total) {
-      if (pos >= rend) {
-        do {
-          r++;
-          rend = off[r + 1];
-        } while (pos >= rend);
-        ro = load_rec(v, c, r);
-        p = 0;
+    for (int b = 0; b < 16; b++) {
+      const u64 pos = o + (u64)b;
+      if (pos < total) {
+        if (pos >= rend) {
+          do {
+            r++;
+            rend = off[r + 1];
+          } while (pos >= rend);
+          ro = load_rec(v, c, r);
+          p = 0;
+        }
+        w[b >> 2] |= (u32)rec_byte(v, c, ro, p, lut) << (8 * (b & 3));
+        p++;
       }
-      w[b >> 2] |= (u32)rec_byte(v, c, ro, p, lut) << (8 * (b & 3));
-      p++;
     }
+    *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- records whose formatted text IS their input text ("@h\ns\n+\nq\n" / ">h\ns\n" on one line): rmdup, grep and
+// seq-with-filters then only compact byte ranges.  k_contig_check counts the kept records that are not of that kind.
+__global__ void k_contig_check(RecViews v, EmitCfg c, const u8 *__restrict__ keep, int fastq, u32 in_bytes,
+                               unsigned long long *n_bad) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= v.n_rec) return;
+  if (keep && !keep[r]) return;
+  const u32 no = v.name_off[r], nl = v.name_len[r], so = v.seq_off[r], sl = v.seq_len[r];
+  // "<marker>name\n" directly in front of the sequence, and the sequence view is the whole line
+  bool ok = no >= 1 && v.in[no - 1] == c.marker && so == no + nl + 1;
+  if (fastq) {
+    const u32 qo = v.qual_off[r];
+    ok = ok && v.qual_len[r] == sl && qo == so + sl + 3 && v.in[so + sl] == '\n' && v.in[so + sl + 1] == '+' &&
+         v.in[so + sl + 2] == '\n' && (qo + sl >= in_bytes || v.in[qo + sl] == '\n');
+  } else {
+    ok = ok && wrap_len(sl, c.width) == sl && (so + sl >= in_bytes || v.in[so + sl] == '\n');
+  }
+  if (!ok) atomicAdd(n_bad, 1ull);
+}
+
+// 16 output bytes per thread and step, each gathered from at most a few records' contiguous source ranges:
+// five aligned 32-bit loads + funnel shifts give the 16-byte window at any source alignment
+__device__ __forceinline__ uint4 load_window(const u8 *__restrict__ base, u64 src, u32 in_bytes) {
+  const u64 a0 = src & ~3ull;
+  const u32 *w = reinterpret_cast<const u32 *>(base + a0);
+  const u32 sh = (u32)(src & 3ull) * 8u;
+  u32 a, b, cc, d, e;
+  if (a0 + 20 <= (u64)in_bytes) {
+    a = w[0]; b = w[1]; cc = w[2]; d = w[3]; e = w[4];
+  } else {  // last bytes of the input: whole words only where the word starts inside it (the buffer is 16-byte aligned)
+    a = a0 < in_bytes ? w[0] : 0u;
+    b = a0 + 4 < in_bytes ? w[1] : 0u;
+    cc = a0 + 8 < in_bytes ? w[2] : 0u;
+    d = a0 + 12 < in_bytes ? w[3] : 0u;
+    e = a0 + 16 < in_bytes ? w[4] : 0u;
+  }
+  return make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, cc, sh), __funnelshift_r(cc, d, sh), __funnelshift_r(d, e, sh));
+}
+
+__global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__restrict__ off, u8 *__restrict__ out, u64 total,
+                                                     u32 in_bytes) {
+  __shared__ u32 s_r[2];
+  const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
+  cta_record_range(off, v.n_rec, o0, total, s_r);
+  for (u32 ch = 0; ch < kEmitChunks; ch++) {
+    const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
+    if (o >= total) return;
+    u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
+    u64 rbeg = off[r], rend = off[r + 1];
+    u32 w[4] = {0, 0, 0, 0};
+    u64 pos = o;
+    const u64 oend = o + 16 < total ? o + 16 : total;
+    while (pos < oend) {
+      while (pos >= rend) {  // next record with output (dropped ones have no bytes)
+        r++;
+        rbeg = rend;
+        rend = off[r + 1];
+      }
+      // bytes [pos, seg_end) of the chunk come from record r, whose text starts one byte before its name
+      const u64 seg_end = rend < oend ? rend : oend;
+      const u64 src = (u64)(v.name_off[r] - 1u) + (pos - rbeg);
+      const u32 shift = (u32)(pos - o);                 // first chunk byte this record supplies
+      const u32 cnt = (u32)(seg_end - pos);
+      // window aligned to the chunk start; src >= pos >= shift, and bytes in front of the record are masked out below
+      const uint4 win = load_window(v.in, src - shift, in_bytes);
+      u32 ww[4] = {win.x, win.y, win.z, win.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int lo = (int)shift - 4 * q, hi = (int)(shift + cnt) - 4 * q;  // bytes [lo, hi) of word q are taken
+        if (hi <= 0 || lo >= 4) continue;
+        u32 m = 0xffffffffu;
+        if (lo > 0) m &= 0xffffffffu << (8 * lo);
+        if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+        w[q] |= ww[q] & m;
+      }
+      pos = seg_end;
+    }
+    *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 void out_len(RecViews v, EmitCfg c, const u8 *keep, u32 *out_len_, cudaStream_t s) {
@@ -116,8 +237,17 @@ void out_len(RecViews v, EmitCfg c, const u8 *keep, u32 *out_len_, cudaStream_t 
 }
 void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, cudaStream_t s) {
   if (!total) return;
-  const u64 threads = (total + 15) / 16;
-  BSK_LAUNCH_FLAT(k_emit, (u32)((threads + 255) / 256), 256, 0, s, v, c, out_off, out, total, lut);
+  const u64 per_cta = 256ull * 16 * kEmitChunks;
+  BSK_LAUNCH(k_emit, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, c, out_off, out, total, lut);
+}
+void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes, u64 *n_bad, cudaStream_t s) {
+  if (v.n_rec)
+    BSK_LAUNCH_FLAT(k_contig_check, (v.n_rec + 255) / 256, 256, 0, s, v, c, keep, fastq, in_bytes, (unsigned long long *)n_bad);
+}
+void emit_contig(RecViews v, const u64 *out_off, u8 *out, u64 total, u32 in_bytes, cudaStream_t s) {
+  if (!total) return;
+  const u64 per_cta = 256ull * 16 * kEmitChunks;
+  BSK_LAUNCH(k_emit_contig, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, out_off, out, total, in_bytes);
 }
 
 }  // namespace k

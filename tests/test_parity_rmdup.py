@@ -6,7 +6,7 @@ import pytest
 import oracle
 from bigseqkit_b200.api import BskError, Operator
 from cases import EDGE_INPUTS, FQ_SIMPLE, fuzz_fasta, fuzz_fastq
-from util import check_parity
+from util import check_parity, run_lib, run_oracle
 
 RMDUP_OPTS = [{}, {"BySeq": True}, {"ByName": True}, {"BySeq": True, "IgnoreCase": True}, {"IgnoreCase": True},
               {"BySeq": True, "OnlyPositiveStrand": True}, {"BySeq": True, "Config": {"LineWidth": 7}},
@@ -90,3 +90,23 @@ def test_rmdup_multi_block_partition(lib, monkeypatch):
         r = o.call(data)
         assert r.data == exp[0] and list(r.elem_off) == exp[1]
         assert o.rmdup_removed() == exp[2]
+
+
+def test_rmdup_compacts_byte_ranges_like_the_formatter(lib, monkeypatch):
+    # k_emit_contig (records printed as they stand) against k_emit (byte-wise formatter) and the oracle
+    from bigseqkit_b200 import synth
+    base = synth.fastq_reads(120 << 10, seed=81, dup_frac=0.3).tobytes()
+    cases = {
+        "plain": base,
+        "no_final_newline": base[:-1],
+        "last_record_is_a_duplicate": base + base[:base.index(b"\n@", 10) + 1],
+        "fasta_single_line": synth.fasta_reads(1500, read_len=50, seed=82).tobytes() * 2,
+    }
+    for name, data in cases.items():
+        exp = run_oracle("RmDup", data, {"BySeq": True})
+        got = run_lib(lib, "RmDup", data, {"BySeq": True})
+        assert got[0] == exp[0] and list(got[1]) == list(exp[1]), name
+        monkeypatch.setenv("BSK_NO_CONTIG", "1")
+        got2 = run_lib(lib, "RmDup", data, {"BySeq": True})
+        monkeypatch.delenv("BSK_NO_CONTIG")
+        assert got2[0] == exp[0] and list(got2[1]) == list(exp[1]), name
