@@ -174,13 +174,23 @@ int Engine::prepare_block(const u8 *d_in, u32 n) {
     u8 *h2 = h_small_.as<u8>();
     BSK_CUDA(cudaMemcpyAsync(h2, sa + n_rec_, 4, cudaMemcpyDeviceToHost, stream));
     BSK_CUDA(cudaMemcpyAsync(h2 + 4, qa + n_rec_, 4, cudaMemcpyDeviceToHost, stream));
+    const bool try_uniform = !fastq_ && getenv("BSK_NO_UNIFORM_SQUEEZE") == nullptr;
+    if (try_uniform) {  // FASTA wrapped at a fixed width (every writer's output): no per-line work needed
+      BSK_CUDA(cudaMemsetAsync(&d_status_->counters[7], 0, 8, stream));
+      k::lines_uniform(ix_, &d_status_->counters[7], stream);
+      launches_++;
+      BSK_CUDA(cudaMemcpyAsync(h2 + 8, &d_status_->counters[7], 8, cudaMemcpyDeviceToHost, stream));
+    }
     BSK_CUDA(cudaStreamSynchronize(stream));
     u32 stot, qtot;
     memcpy(&stot, h2, 4);
     memcpy(&qtot, h2 + 4, 4);
+    u64 ragged = 1;
+    if (try_uniform) memcpy(&ragged, h2 + 8, 8);
     u8 *sar = b_seq_arena_.get<u8>((size_t)stot + 64);
     u8 *qar = b_qual_arena_.get<u8>((size_t)qtot + 64);
-    k::squeeze_lines(ix_, ra_, sa, qa, sar, qar, stream);
+    if (ragged == 0) k::squeeze_uniform(ix_, ra_, sa, sar, stot, stream);
+    else k::squeeze_lines(ix_, ra_, sa, qa, sar, qar, stream);
     launches_++;
     squeezed_ = true;
     seq_space_ = stot;

@@ -226,6 +226,116 @@ __global__ void k_squeeze_lines(RecIndex ix, RecArrays ra, const u32 *__restrict
   for (u32 i = lane; i < len; i += 32) dst[i] = src[i];
 }
 
+// ---------------------------------------------------------------- uniformly wrapped FASTA: arithmetic squeeze
+// A record whose sequence lines all have the same width W except the last (<= W) -- what every FASTA writer
+// produces -- needs no per-line work: byte q of its squeezed sequence is input byte seq_start + q + q / W.
+// k_lines_uniform counts the lines that break that rule (FASTA only: a header is line 0 or a line starting '>').
+__global__ void k_lines_uniform(RecIndex ix, unsigned long long *n_bad) {
+  const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 || j >= ix.n_lines) return;
+  const u8 *__restrict__ d = ix.in;
+  const u32 *__restrict__ ls = ix.ls;
+  const u32 a = ls[j], pa = ls[j - 1];
+  const bool hdr = a < ix.n && d[a] == '>';
+  const bool prev_hdr = j - 1 == 0 || d[pa] == '>';
+  if (hdr || prev_hdr) return;  // headers and first sequence lines set no constraint
+  const u32 len = ls[j + 1] - 1 - a, plen = a - 1 - pa;
+  const bool last = j + 1 >= ix.n_lines || (ls[j + 1] < ix.n && d[ls[j + 1]] == '>');
+  if (last ? len > plen : len != plen) atomicAdd(n_bad, 1ull);
+}
+
+__device__ __forceinline__ u32 warp_search_u32(const u32 *__restrict__ off, u32 n, u32 o) {  // last r with off[r] <= o
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const u32 step = (hi - lo + 32) / 33;
+    const u32 idx = lo + (lane + 1) * step;
+    const bool le = idx < hi && off[idx] <= o;
+    const u32 cnt = (u32)__popc(__ballot_sync(0xffffffffu, le));
+    const u32 nhi = lo + (cnt + 1) * step;
+    lo += cnt * step;
+    if (nhi < hi) hi = nhi;
+  }
+  return lo;
+}
+
+// 16 arena bytes per thread and step (aligned 16-byte stores); each run of bytes inside one input line is one
+// unaligned 16-byte window (five aligned word loads + funnel shifts), masked into place
+__global__ void __launch_bounds__(256) k_squeeze_uniform(RecIndex ix, RecArrays ra, const u32 *__restrict__ seq_aoff,
+                                                         u8 *__restrict__ seq_arena, u32 total) {
+  __shared__ u32 s_r[2];
+  const u32 cta0 = blockIdx.x * 256u * 16u * 4u;
+  if (threadIdx.x < 64) {
+    const u32 w = threadIdx.x >> 5;
+    u32 o = w == 0 ? cta0 : cta0 + 256u * 16u * 4u - 1u;
+    if (o >= total) o = total - 1;
+    const u32 r = warp_search_u32(seq_aoff, ix.n_rec, o);
+    if ((threadIdx.x & 31) == 0) s_r[w] = r;
+  }
+  __syncthreads();
+  const u8 *__restrict__ in = ix.in;
+  for (u32 ch = 0; ch < 4; ch++) {
+    const u32 o = cta0 + (ch * 256u + threadIdx.x) * 16u;
+    if (o >= total) return;
+    u32 lo = s_r[0], hi = s_r[1] + 1;  // seq_aoff[lo] <= o < seq_aoff[hi]
+    while (hi - lo > 1) {
+      const u32 mid = lo + ((hi - lo) >> 1);
+      if (seq_aoff[mid] <= o) lo = mid;
+      else hi = mid;
+    }
+    u32 r = lo;
+    u32 rbeg = seq_aoff[r], rend = seq_aoff[r + 1];
+    u32 w[4] = {0, 0, 0, 0};
+    u32 pos = o;
+    const u32 oend = o + 16 < total ? o + 16 : total;
+    u32 sstart = 0, W = 1;
+    bool have = false;
+    while (pos < oend) {
+      if (pos >= rend || !have) {
+        while (pos >= rend) {  // next record with sequence bytes
+          r++;
+          rbeg = rend;
+          rend = seq_aoff[r + 1];
+        }
+        const u32 sa = ra.seq_line0[r];
+        sstart = ix.ls[sa];
+        W = ix.ls[sa + 1] - 1 - sstart;  // width of the record's lines (> 0: the record has sequence bytes)
+        have = true;
+      }
+      const u32 qr = pos - rbeg;
+      const u32 line = qr / W, col = qr - line * W;
+      u32 cnt = W - col;                                // bytes left on this input line
+      if (cnt > rend - pos) cnt = rend - pos;
+      if (cnt > oend - pos) cnt = oend - pos;
+      const u32 src = sstart + qr + line;
+      const u32 shift = pos - o;
+      // window aligned to the chunk start (src >= shift: the header line precedes the sequence)
+      const u32 s0 = src - shift, a0 = s0 & ~3u, sh = (s0 & 3u) * 8u;
+      const u32 *wp = reinterpret_cast<const u32 *>(in + a0);
+      u32 x0, x1, x2, x3, x4;
+      if (a0 + 20 <= ix.n) { x0 = wp[0]; x1 = wp[1]; x2 = wp[2]; x3 = wp[3]; x4 = wp[4]; }
+      else {
+        x0 = a0 < ix.n ? wp[0] : 0u; x1 = a0 + 4 < ix.n ? wp[1] : 0u; x2 = a0 + 8 < ix.n ? wp[2] : 0u;
+        x3 = a0 + 12 < ix.n ? wp[3] : 0u; x4 = a0 + 16 < ix.n ? wp[4] : 0u;
+      }
+      const u32 ww[4] = {__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                         __funnelshift_r(x3, x4, sh)};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int l = (int)shift - 4 * q, h = (int)(shift + cnt) - 4 * q;  // bytes [l, h) of word q are taken
+        if (h <= 0 || l >= 4) continue;
+        u32 m = 0xffffffffu;
+        if (l > 0) m &= 0xffffffffu << (8 * l);
+        if (h < 4) m &= 0xffffffffu >> (8 * (4 - h));
+        w[q] |= ww[q] & m;
+      }
+      pos += cnt;
+    }
+    if (o + 16 <= total) *reinterpret_cast<uint4 *>(seq_arena + o) = make_uint4(w[0], w[1], w[2], w[3]);
+    else for (u32 t = 0; o + t < total; t++) seq_arena[o + t] = (u8)(w[t >> 2] >> (8 * (t & 3)));
+  }
+}
+
 // ---------------------------------------------------------------- alphabet guess on record 0
 __global__ void k_guess_alphabet(RecViews v, const u8 *__restrict__ class_mask, u32 limit, DevStatus *st) {
   if (v.n_rec == 0) return;
@@ -317,6 +427,14 @@ void squeeze_lines(RecIndex ix, RecArrays ra, const u32 *seq_aoff, const u32 *qu
   const u64 threads = (u64)ix.n_lines * 32;
   BSK_LAUNCH_FLAT(k_squeeze_lines, (u32)((threads + 255) / 256), 256, 0, s, ix, ra, seq_aoff, qual_aoff, seq_arena,
                   qual_arena);
+}
+void lines_uniform(RecIndex ix, u64 *n_bad, cudaStream_t s) {
+  if (ix.n_lines > 1) BSK_LAUNCH_FLAT(k_lines_uniform, (ix.n_lines + 255) / 256, 256, 0, s, ix, (unsigned long long *)n_bad);
+}
+void squeeze_uniform(RecIndex ix, RecArrays ra, const u32 *seq_aoff, u8 *seq_arena, u32 total, cudaStream_t s) {
+  if (!total) return;
+  const u32 per_cta = 256u * 16u * 4u;
+  BSK_LAUNCH(k_squeeze_uniform, (total + per_cta - 1) / per_cta, 256, 0, s, ix, ra, seq_aoff, seq_arena, total);
 }
 void guess_alphabet(RecViews v, const u8 *class_mask, u32 limit, DevStatus *st, cudaStream_t s) {
   BSK_LAUNCH_FLAT(k_guess_alphabet, 1, 256, 0, s, v, class_mask, limit, st);

@@ -77,6 +77,10 @@ void index_finish(u32 *ls, u32 *rl, u32 n, u32 n_nl, u32 n_rec, u32 n_lines, cud
 void parse_records(RecIndex ix, RecArrays ra, DevStatus *st, cudaStream_t s);
 void squeeze_lines(RecIndex ix, RecArrays ra, const u32 *seq_aoff, const u32 *qual_aoff, u8 *seq_arena, u8 *qual_arena,
                    cudaStream_t s);
+// uniformly wrapped FASTA: count the lines that break "all lines of a record as wide as its first, the last <= that",
+// then squeeze arithmetically (byte q of a record's sequence = input byte seq_start + q + q / W)
+void lines_uniform(RecIndex ix, u64 *n_bad, cudaStream_t s);
+void squeeze_uniform(RecIndex ix, RecArrays ra, const u32 *seq_aoff, u8 *seq_arena, u32 total, cudaStream_t s);
 void guess_alphabet(RecViews v, const u8 *class_mask, u32 limit, DevStatus *st, cudaStream_t s);
 void id_desc(RecViews v, int id_ncbi, u32 *id_off, u32 *id_len, u32 *desc_off, u32 *desc_len, cudaStream_t s);
 void validate_seq(RecViews v, const u8 *valid, u32 limit, DevStatus *st, cudaStream_t s);

@@ -10,7 +10,8 @@ namespace bsk {
 struct Engine::RmdupState {
   // key -> earliest global record ordinal; open addressing, cap slots + 1 extra slot for key 0
   u64 *tkeys = nullptr, *tfirst = nullptr;
-  u64 cap = 0;
+  u64 cap = 0, alloc_cap = 0;
+  bool dirty = false;  // holds keys of a partition that has been reset
   // {xxh64 seed 0, xxh64 seed B} of every record of the partition seen so far (global input order)
   u64 *hist_keys = nullptr, *hist_fp = nullptr;
   u64 n_hist = 0, hist_cap = 0;

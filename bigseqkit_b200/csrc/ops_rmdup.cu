@@ -148,16 +148,21 @@ static void hist_reserve(Engine::RmdupState *rm, u64 need, cudaStream_t s) {
 }
 
 static void table_reserve(Engine::RmdupState *rm, u64 total, cudaStream_t s, u64 &launches) {
-  if (rm->cap && total * 2 <= rm->cap) return;
+  if (rm->cap && !rm->dirty && total * 2 <= rm->cap) return;
   u64 cap = 1u << 12;
   while (cap < total * 4) cap *= 2;
-  if (rm->tkeys) cudaFree(rm->tkeys);
-  if (rm->tfirst) cudaFree(rm->tfirst);
-  BSK_CUDA(cudaMalloc((void **)&rm->tkeys, (cap + 1) * 8));
-  BSK_CUDA(cudaMalloc((void **)&rm->tfirst, (cap + 1) * 8));
+  if (cap > rm->alloc_cap) {  // device memory is kept across bsk_reset / partitions: only growth reallocates
+    if (rm->tkeys) cudaFree(rm->tkeys);
+    if (rm->tfirst) cudaFree(rm->tfirst);
+    rm->tkeys = rm->tfirst = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&rm->tkeys, (cap + 1) * 8));
+    BSK_CUDA(cudaMalloc((void **)&rm->tfirst, (cap + 1) * 8));
+    rm->alloc_cap = cap;
+  }
   BSK_CUDA(cudaMemsetAsync(rm->tkeys, 0, (cap + 1) * 8, s));
   BSK_CUDA(cudaMemsetAsync(rm->tfirst, 0xff, (cap + 1) * 8, s));
   rm->cap = cap;
+  rm->dirty = false;
   if (rm->n_hist) {
     BSK_LAUNCH_FLAT(k_table_insert, (u32)((rm->n_hist + 255) / 256), 256, 0, s, rm->hist_keys, rm->n_hist, (u64)0, rm->tkeys,
                     rm->tfirst, cap);
@@ -177,10 +182,7 @@ void rmdup_state_free(Engine::RmdupState *rm) {
 void rmdup_state_reset(Engine::RmdupState *rm) {
   if (!rm) return;
   rm->n_hist = 0;
-  if (rm->tkeys) cudaFree(rm->tkeys);
-  if (rm->tfirst) cudaFree(rm->tfirst);
-  rm->tkeys = rm->tfirst = nullptr;
-  rm->cap = 0;
+  rm->dirty = true;  // the table is cleared (not freed) before its next use
   rm->block_ready = false;
 }
 

@@ -40,14 +40,46 @@ __global__ void k_tr_len(RecViews v, TrCfg c, u32 *__restrict__ plen, DevStatus 
   plen[e] = (l - start) / 3;
 }
 
-// one thread per 4 consecutive amino acids of the arena
+// One thread per 16 consecutive amino acids of the arena (one aligned 16-byte store); the CTA finds the range of
+// (record, frame) elements it covers once with two warp-wide searches, the code tables live in shared memory.
+static const u32 kTrAA = 16;
+
+__device__ __forceinline__ u32 tr_warp_search(const u64 *__restrict__ off, u32 n, u64 o) {  // last e with off[e] <= o
+  const u32 lane = threadIdx.x & 31;
+  u32 lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const u32 step = (hi - lo + 32) / 33;
+    const u32 idx = lo + (lane + 1) * step;
+    const bool le = idx < hi && off[idx] <= o;
+    const u32 cnt = (u32)__popc(__ballot_sync(0xffffffffu, le));
+    const u32 nhi = lo + (cnt + 1) * step;
+    lo += cnt * step;
+    if (nhi < hi) hi = nhi;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u64 *__restrict__ poff, u64 total,
                                                    const u8 *__restrict__ code_fwd, const u8 *__restrict__ code_rev,
                                                    const u8 *__restrict__ lut, u8 *__restrict__ prot, DevStatus *st) {
-  const u64 a0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4ull;
-  if (a0 >= total) return;
+  __shared__ u8 s_fwd[256], s_rev[256], s_lut[4096];
+  __shared__ u32 s_e[2];
+  s_fwd[threadIdx.x] = code_fwd[threadIdx.x];
+  s_rev[threadIdx.x] = code_rev[threadIdx.x];
+  for (u32 i = threadIdx.x; i < 4096; i += 256) s_lut[i] = lut[i];
   const u32 n_el = v.n_rec * c.nf;
-  u32 lo = 0, hi = n_el;  // poff[lo] <= a0 < poff[hi]
+  const u64 cta0 = (u64)blockIdx.x * 256ull * kTrAA;
+  if (threadIdx.x < 64) {
+    const u32 w = threadIdx.x >> 5;
+    u64 o = w == 0 ? cta0 : cta0 + 256ull * kTrAA - 1;
+    if (o >= total) o = total - 1;
+    const u32 e = tr_warp_search(poff, n_el, o);
+    if ((threadIdx.x & 31) == 0) s_e[w] = e;
+  }
+  __syncthreads();
+  const u64 a0 = cta0 + (u64)threadIdx.x * kTrAA;
+  if (a0 >= total) return;
+  u32 lo = s_e[0], hi = s_e[1] + 1;  // poff[lo] <= a0 < poff[hi]
   while (hi - lo > 1) {
     const u32 mid = lo + ((hi - lo) >> 1);
     if (poff[mid] <= a0) lo = mid;
@@ -56,47 +88,60 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
   u32 e = lo;
   u64 eend = poff[e + 1];
   u32 j = (u32)(a0 - poff[e]);
-  for (int t = 0; t < 4; t++) {
+  // element state, refreshed whenever the arena position crosses into the next (record, frame)
+  u32 r = e / c.nf;
+  int f = c.frames[e - r * c.nf];
+  u32 start = (u32)((f < 0 ? -f : f) - 1), l = v.seq_len[r];
+  const u8 *s = v.seqb + v.seq_off[r];
+  u32 w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int t = 0; t < (int)kTrAA; t++) {
     const u64 a = a0 + (u64)t;
-    if (a >= total) break;
-    if (a >= eend) {
-      do {
-        e++;
-        eend = poff[e + 1];
-      } while (a >= eend);
-      j = 0;
+    if (a < total) {
+      if (a >= eend) {
+        do {
+          e++;
+          eend = poff[e + 1];
+        } while (a >= eend);
+        j = 0;
+        r = e / c.nf;
+        f = c.frames[e - r * c.nf];
+        start = (u32)((f < 0 ? -f : f) - 1);
+        l = v.seq_len[r];
+        s = v.seqb + v.seq_off[r];
+      }
+      const u32 i = start + 3u * j;
+      u32 c0, c1, c2;
+      if (f > 0) {
+        c0 = s_fwd[s[i]];
+        c1 = s_fwd[s[i + 1]];
+        c2 = s_fwd[s[i + 2]];
+      } else {  // codon i of the reverse complement
+        c0 = s_rev[s[l - 1 - i]];
+        c1 = s_rev[s[l - 2 - i]];
+        c2 = s_rev[s[l - 3 - i]];
+      }
+      u8 aa;
+      bool init = false;
+      if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
+      else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
+        aa = 'X';
+        if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
+      } else {
+        const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
+        aa = x & 0x7f;
+        init = (x & 0x80) != 0;
+      }
+      if (c.init_m && j == 0 && init) aa = 'M';
+      if (c.clean && aa == '*') aa = 'X';
+      w[t >> 2] |= (u32)aa << (8 * (t & 3));
+      j++;
     }
-    const u32 r = e / c.nf, fi = e - r * c.nf;
-    const int f = c.frames[fi];
-    const u32 start = (u32)((f < 0 ? -f : f) - 1);
-    const u32 l = v.seq_len[r];
-    const u8 *s = v.seqb + v.seq_off[r];
-    const u32 i = start + 3u * j;
-    u32 c0, c1, c2;
-    if (f > 0) {
-      c0 = code_fwd[s[i]];
-      c1 = code_fwd[s[i + 1]];
-      c2 = code_fwd[s[i + 2]];
-    } else {  // codon i of the reverse complement
-      c0 = code_rev[s[l - 1 - i]];
-      c1 = code_rev[s[l - 2 - i]];
-      c2 = code_rev[s[l - 3 - i]];
-    }
-    u8 aa;
-    bool init = false;
-    if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
-    else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
-      aa = 'X';
-      if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
-    } else {
-      const u8 x = lut[(c0 << 8) | (c1 << 4) | c2];
-      aa = x & 0x7f;
-      init = (x & 0x80) != 0;
-    }
-    if (c.init_m && j == 0 && init) aa = 'M';
-    if (c.clean && aa == '*') aa = 'X';
-    prot[a] = aa;
-    j++;
+  }
+  if (a0 + kTrAA <= total) {
+    *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (u32 t = 0; a0 + t < total; t++) prot[a0 + t] = (u8)(w[t >> 2] >> (8 * (t & 3)));
   }
 }
 
@@ -235,8 +280,8 @@ int Engine::op_translate(BlockOut &bo) {
   u8 *prot = b_op4_.get<u8>((size_t)ptotal + 64);
   if (ptotal) {
     main_begin();
-    BSK_LAUNCH_FLAT(k_translate, (u32)(((ptotal + 3) / 4 + 255) / 256), 256, 0, stream, views_, c, poff, ptotal, d_tab,
-                    d_tab + 256, d_tab + 512, prot, d_status_);
+    BSK_LAUNCH(k_translate, (u32)((ptotal + 256ull * kTrAA - 1) / (256ull * kTrAA)), 256, 0, stream, views_, c, poff, ptotal,
+               d_tab, d_tab + 256, d_tab + 512, prot, d_status_);
     main_end();
     launches_++;
     fetch_status();

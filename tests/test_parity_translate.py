@@ -61,3 +61,21 @@ def test_translate_kat(lib):
             r = o.call((">c\nATG%s\n" % codon).encode())
         assert r.data == (">c\nM%s\n" % aa).encode(), codon
         assert oracle.translate_codon(1, codon) == aa
+
+
+def test_translate_wrapped_fasta_both_squeeze_paths(lib, monkeypatch):
+    # uniformly wrapped records take the arithmetic squeeze (k_squeeze_uniform), ragged ones the per-line copy
+    from bigseqkit_b200 import synth
+    from util import run_lib, run_oracle
+    uniform = synth.fasta_cds(200 << 10, seed=91).tobytes()
+    ragged = uniform.replace(b"\n", b"\n\n", 1) + b">r\nACGTACGTAC\nACG\nACGTACGTACGT\n"
+    long_last = b">a\nATGGCC\nTAA\n>b\nATG\nGCCTAA\n"  # second record: last line longer than the first -> ragged
+    for name, data in (("uniform", uniform), ("uniform_no_final_newline", uniform[:-1]), ("ragged", ragged), ("long_last", long_last)):
+        exp = run_oracle("Translate", data, {"Frame": ["6"]})
+        for env in (None, "1"):
+            if env:
+                monkeypatch.setenv("BSK_NO_UNIFORM_SQUEEZE", env)
+            got = run_lib(lib, "Translate", data, {"Frame": ["6"]})
+            if env:
+                monkeypatch.delenv("BSK_NO_UNIFORM_SQUEEZE")
+            assert got[0] == exp[0] and list(got[1]) == list(exp[1]), (name, env)
