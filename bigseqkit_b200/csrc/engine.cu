@@ -309,7 +309,11 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
     k::emit_contig(views_, ooff, out, total, n_, stream);
     if (total) BSK_CUDA(cudaMemsetAsync(out + total - 1, '\n', 1, stream));  // input without a final newline
   } else {
-    k::emit(views_, cfg, ooff, out, total, lut, stream);
+    // 16-byte windows may over-read a source by up to 19 bytes: fine inside the ctx's own buffers (all carry 64
+    // bytes of slack), not inside the caller's input
+    const u64 no_limit = ~0ull;
+    k::emit(views_, cfg, ooff, out, total, lut, views_.in == in_ ? (u64)n_ : no_limit,
+            views_.seqb == in_ ? (u64)n_ : no_limit, views_.qualb == in_ ? (u64)n_ : no_limit, stream);
   }
   main_end();
   launches_++;

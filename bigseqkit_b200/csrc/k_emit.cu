@@ -118,11 +118,106 @@ __device__ __forceinline__ u32 search_in(const u64 *__restrict__ off, u32 lo, u3
   return lo;
 }
 
+// 16-byte window of base[src .. src+16) at any alignment: five aligned word loads + funnel shifts.  Words that
+// start at or beyond `limit` are not touched (read as 0).
+__device__ __forceinline__ void window16(const u8 *__restrict__ base, u64 src, u64 limit, u32 ww[4]) {
+  const u64 a0 = src & ~3ull;
+  const u32 *w = reinterpret_cast<const u32 *>(base + a0);
+  const u32 sh = (u32)(src & 3ull) * 8u;
+  u32 a, b, cc, d, e;
+  if (a0 + 20 <= limit) {
+    a = w[0]; b = w[1]; cc = w[2]; d = w[3]; e = w[4];
+  } else {
+    a = a0 < limit ? w[0] : 0u;
+    b = a0 + 4 < limit ? w[1] : 0u;
+    cc = a0 + 8 < limit ? w[2] : 0u;
+    d = a0 + 12 < limit ? w[3] : 0u;
+    e = a0 + 16 < limit ? w[4] : 0u;
+  }
+  ww[0] = __funnelshift_r(a, b, sh);
+  ww[1] = __funnelshift_r(b, cc, sh);
+  ww[2] = __funnelshift_r(cc, d, sh);
+  ww[3] = __funnelshift_r(d, e, sh);
+}
+
+// OR bytes [shift, shift + cnt) of the window ww into the chunk words w
+__device__ __forceinline__ void merge16(u32 w[4], const u32 ww[4], u32 shift, u32 cnt) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int l = (int)shift - 4 * q, h = (int)(shift + cnt) - 4 * q;  // bytes [l, h) of word q are taken
+    if (h <= 0 || l >= 4) continue;
+    u32 m = 0xffffffffu;
+    if (l > 0) m &= 0xffffffffu << (8 * l);
+    if (h < 4) m &= 0xffffffffu >> (8 * (4 - h));
+    w[q] |= ww[q] & m;
+  }
+}
+
+// The piece of record output that starts at position p of the record: a literal byte, a run copied straight from a
+// source buffer, or a run that needs the byte path (reversed and / or mapped sequence).
+struct Piece {
+  u32 len;        // bytes in the piece from p on (>= 1)
+  int kind;       // 0 literal, 1 straight copy, 2 byte path
+  u8 lit;
+  const u8 *base; // kind 1: source buffer and offset of the first byte
+  u64 src;
+};
+
+__device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, const RecOut &o, u32 p, bool seq_plain) {
+  Piece pc;
+  pc.base = nullptr;
+  pc.src = 0;
+  if (p < o.np) {
+    u32 q = p;
+    if (c.marker) {
+      if (q == 0) { pc.kind = 0; pc.len = 1; pc.lit = c.marker; return pc; }
+      q--;
+    }
+    if (q < o.name_len) { pc.kind = 1; pc.len = o.name_len - q; pc.base = v.in; pc.src = (u64)o.name_off + q; return pc; }
+    pc.kind = 0; pc.len = 1; pc.lit = '\n';
+    return pc;
+  }
+  p -= o.np;
+  if (p < o.ns) {
+    if (p == o.wl) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
+    u32 j = p, run = o.seq_len - p;
+    if (c.width > 0) {
+      const u32 line = p / (c.width + 1u), col = p - line * (c.width + 1u);
+      if (col == c.width) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
+      j = line * c.width + col;
+      run = c.width - col;
+      if (run > o.seq_len - j) run = o.seq_len - j;
+    }
+    pc.len = run;
+    if (seq_plain) { pc.kind = 1; pc.base = v.seqb; pc.src = (u64)o.seq_off + j; }
+    else pc.kind = 2;
+    return pc;
+  }
+  p -= o.ns;
+  if (c.plus_line) {
+    if (p == 0) { pc.kind = 0; pc.len = 1; pc.lit = '+'; return pc; }
+    if (p == 1) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
+    p -= 2;
+  }
+  if (p < o.qual_len) {
+    pc.len = o.qual_len - p;
+    if (!c.reverse) { pc.kind = 1; pc.base = v.qualb; pc.src = (u64)o.qual_off + p; }
+    else pc.kind = 2;
+    return pc;
+  }
+  pc.kind = 0; pc.len = 1; pc.lit = '\n';
+  return pc;
+}
+
+// One aligned 16-byte store per thread and step.  Runs that are plain copies of source bytes (names, unreversed
+// sequence / quality lines, translated proteins) move as 16-byte windows; only reversed or mapped sequence bytes
+// and single literal bytes are assembled byte by byte.
 __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
-                                              u64 total, const u8 *__restrict__ lut) {
+                                              u64 total, const u8 *__restrict__ lut, u64 in_limit, u64 seq_limit, u64 qual_limit) {
   __shared__ u32 s_r[2];
   const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
   cta_record_range(off, v.n_rec, o0, total, s_r);
+  const bool seq_plain = !c.reverse && lut == nullptr;
   for (u32 ch = 0; ch < kEmitChunks; ch++) {
     const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
     if (o >= total) return;
@@ -131,21 +226,33 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
     u64 rend = off[r + 1];
     u32 p = (u32)(o - off[r]);
     u32 w[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int b = 0; b < 16; b++) {
-      const u64 pos = o + (u64)b;
-      if (pos < total) {
-        if (pos >= rend) {
-          do {
-            r++;
-            rend = off[r + 1];
-          } while (pos >= rend);
-          ro = load_rec(v, c, r);
-          p = 0;
-        }
-        w[b >> 2] |= (u32)rec_byte(v, c, ro, p, lut) << (8 * (b & 3));
-        p++;
+    u64 pos = o;
+    const u64 oend = o + 16 < total ? o + 16 : total;
+    while (pos < oend) {
+      if (pos >= rend) {
+        do {
+          r++;
+          rend = off[r + 1];
+        } while (pos >= rend);
+        ro = load_rec(v, c, r);
+        p = 0;
       }
+      const Piece pc = piece_at(v, c, ro, p, seq_plain);
+      u32 cnt = pc.len;
+      if (cnt > oend - pos) cnt = (u32)(oend - pos);
+      const u32 shift = (u32)(pos - o);
+      if (pc.kind == 0) {
+        w[shift >> 2] |= (u32)pc.lit << (8 * (shift & 3));
+      } else if (pc.kind == 1 && pc.src >= shift) {
+        u32 ww[4];
+        const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
+        window16(pc.base, pc.src - shift, limit, ww);
+        merge16(w, ww, shift, cnt);
+      } else {
+        for (u32 t = 0; t < cnt; t++) w[(shift + t) >> 2] |= (u32)rec_byte(v, c, ro, p + t, lut) << (8 * ((shift + t) & 3));
+      }
+      pos += cnt;
+      p += cnt;
     }
     *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -169,25 +276,6 @@ __global__ void k_contig_check(RecViews v, EmitCfg c, const u8 *__restrict__ kee
     ok = ok && wrap_len(sl, c.width) == sl && (so + sl >= in_bytes || v.in[so + sl] == '\n');
   }
   if (!ok) atomicAdd(n_bad, 1ull);
-}
-
-// 16 output bytes per thread and step, each gathered from at most a few records' contiguous source ranges:
-// five aligned 32-bit loads + funnel shifts give the 16-byte window at any source alignment
-__device__ __forceinline__ uint4 load_window(const u8 *__restrict__ base, u64 src, u32 in_bytes) {
-  const u64 a0 = src & ~3ull;
-  const u32 *w = reinterpret_cast<const u32 *>(base + a0);
-  const u32 sh = (u32)(src & 3ull) * 8u;
-  u32 a, b, cc, d, e;
-  if (a0 + 20 <= (u64)in_bytes) {
-    a = w[0]; b = w[1]; cc = w[2]; d = w[3]; e = w[4];
-  } else {  // last bytes of the input: whole words only where the word starts inside it (the buffer is 16-byte aligned)
-    a = a0 < in_bytes ? w[0] : 0u;
-    b = a0 + 4 < in_bytes ? w[1] : 0u;
-    cc = a0 + 8 < in_bytes ? w[2] : 0u;
-    d = a0 + 12 < in_bytes ? w[3] : 0u;
-    e = a0 + 16 < in_bytes ? w[4] : 0u;
-  }
-  return make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, cc, sh), __funnelshift_r(cc, d, sh), __funnelshift_r(d, e, sh));
 }
 
 __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__restrict__ off, u8 *__restrict__ out, u64 total,
@@ -214,18 +302,10 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
       const u64 src = (u64)(v.name_off[r] - 1u) + (pos - rbeg);
       const u32 shift = (u32)(pos - o);                 // first chunk byte this record supplies
       const u32 cnt = (u32)(seg_end - pos);
-      // window aligned to the chunk start; src >= pos >= shift, and bytes in front of the record are masked out below
-      const uint4 win = load_window(v.in, src - shift, in_bytes);
-      u32 ww[4] = {win.x, win.y, win.z, win.w};
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int lo = (int)shift - 4 * q, hi = (int)(shift + cnt) - 4 * q;  // bytes [lo, hi) of word q are taken
-        if (hi <= 0 || lo >= 4) continue;
-        u32 m = 0xffffffffu;
-        if (lo > 0) m &= 0xffffffffu << (8 * lo);
-        if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-        w[q] |= ww[q] & m;
-      }
+      // window aligned to the chunk start; src >= pos >= shift, and bytes in front of the record are masked out
+      u32 ww[4];
+      window16(v.in, src - shift, (u64)in_bytes, ww);
+      merge16(w, ww, shift, cnt);
       pos = seg_end;
     }
     *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -235,10 +315,12 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
 void out_len(RecViews v, EmitCfg c, const u8 *keep, u32 *out_len_, cudaStream_t s) {
   BSK_LAUNCH_FLAT(k_out_len, (v.n_rec + 1 + 255) / 256, 256, 0, s, v, c, keep, out_len_);
 }
-void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, cudaStream_t s) {
+void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, u64 in_limit, u64 seq_limit,
+          u64 qual_limit, cudaStream_t s) {
   if (!total) return;
   const u64 per_cta = 256ull * 16 * kEmitChunks;
-  BSK_LAUNCH(k_emit, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, c, out_off, out, total, lut);
+  BSK_LAUNCH(k_emit, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, c, out_off, out, total, lut, in_limit, seq_limit,
+             qual_limit);
 }
 void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes, u64 *n_bad, cudaStream_t s) {
   if (v.n_rec)

@@ -87,7 +87,9 @@ void validate_seq(RecViews v, const u8 *valid, u32 limit, DevStatus *st, cudaStr
 
 // ---- generic record emitter (k_emit.cu)
 void out_len(RecViews v, EmitCfg c, const u8 *keep, u32 *out_len, cudaStream_t s);
-void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, cudaStream_t s);
+// in_limit / seq_limit / qual_limit: readable bytes of v.in / v.seqb / v.qualb (16-byte windows stop there)
+void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u8 *lut, u64 in_limit, u64 seq_limit,
+          u64 qual_limit, cudaStream_t s);
 // records whose formatted text is their input text: count the kept ones that are not, then compact byte ranges
 void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes, u64 *n_bad, cudaStream_t s);
 void emit_contig(RecViews v, const u64 *out_off, u8 *out, u64 total, u32 in_bytes, cudaStream_t s);

@@ -170,6 +170,24 @@ def _run(fn, data, opts):
     return _take(out, rc)
 
 
+def time_c_call(fn, data, opts):
+    """Wall time of the C function alone (no Python conversion of the result); returns (seconds, out bytes, elements).
+    Used by the CPU-baseline legs of the benches."""
+    import time
+    keep = []
+    o = _mk_opts(opts, keep)
+    out = _Out()
+    t0 = time.perf_counter()
+    rc = getattr(lib(), fn)(data, len(data), C.byref(o), C.byref(out))
+    dt = time.perf_counter() - t0
+    n, ne = out.n, out.n_elem
+    err = out.err.decode(errors="replace")
+    lib().orc_out_free(C.byref(out))
+    if rc != 0:
+        raise OracleError(err)
+    return dt, n, ne
+
+
 def seq(data, opts=None):
     return _run("orc_seq", data, opts)
 

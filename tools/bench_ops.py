@@ -66,15 +66,26 @@ def main():
                 "in_bytes": n, "out_bytes": n_out, "records": n_rec, "ms_per_step": ms, "records_per_s": n_rec / ms * 1e3,
                 "gb_per_s": n / ms / 1e6, "algorithmic_bytes": alg, "whole_step_frac_of_hbm_peak": alg / ms / 1e6 / peak,
                 "gpu_launches_per_step": launches // args.steps, "fused_blocks": op.timings()["fused_blocks"]}
-        if args.cpu and cpu_op:
-            threads = os.cpu_count() or 1
-            sample = np.ascontiguousarray(host[: min(n, 256 << 20)])
+        if args.cpu:
+            # the oracle port of the reference CPU path on a bounded sample of the same input: all host threads where
+            # the port has a sharded driver (seq / stats / rmdup), one thread otherwise
+            cap = (256 << 20) if cpu_op else ((4 << 20) if name == 'locate' else (16 << 20))
+            sample = np.ascontiguousarray(host[: min(n, cap)])
             k = sample.tobytes().rfind(b"\n@" if sample[0] == 0x40 else b"\n>")
             sample = np.ascontiguousarray(sample[: k + 1])
-            t0 = time.perf_counter()
-            nr, _ = oracle.run_mt(cpu_op, sample.ctypes.data, sample.nbytes, opts, threads)
-            dt = time.perf_counter() - t0
-            line["cpu_port"] = {"records_per_s": nr / dt, "gb_per_s": sample.nbytes / dt / 1e9, "cores": threads}
+            if cpu_op:
+                threads = os.cpu_count() or 1
+                t0 = time.perf_counter()
+                nr, _ = oracle.run_mt(cpu_op, sample.ctypes.data, sample.nbytes, opts, threads)
+                dt = time.perf_counter() - t0
+            else:
+                threads = 1
+                sb = sample.tobytes()
+                dt, _, _ = oracle.time_c_call({"translate": "orc_translate", "locate": "orc_locate"}[name], sb, opts)
+                nr = len(oracle.frame(sb)) - 1
+            line["cpu_port"] = {"records_per_s": nr / dt, "gb_per_s": sample.nbytes / dt / 1e9, "cores": threads,
+                                "sample_bytes": int(sample.nbytes)}
+            line["speedup_vs_cpu_port_gbps"] = (n / ms / 1e6) / (sample.nbytes / dt / 1e9)
         print(json.dumps(line), flush=True)
         op.close()
         del d_in

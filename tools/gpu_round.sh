@@ -15,3 +15,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 3 -c 2 -f -o $OUT/${TAG}_prof \
   python bench.py --steps 2 --warmup 3 --block-mib 256 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 tail -5 $OUT/${TAG}_pytest.log; cat $OUT/${TAG}_bench.json; cat $OUT/${TAG}_bench_ref.json; tail -3 $OUT/${TAG}_bench.err
+( timeout 1200 python tools/bench_ops.py --mib 1024 --steps 5 --cpu 2>> $OUT/${TAG}_bench.err ) > $OUT/${TAG}_ops.jsonl
+cut -c1-260 $OUT/${TAG}_ops.jsonl
