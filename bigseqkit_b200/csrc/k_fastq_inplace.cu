@@ -129,15 +129,22 @@ __device__ __forceinline__ void record_inplace(u8 *d, u32 so, u32 sl, u32 qo, co
   const SegGeo S(so, sl), Q(qo, sl);
   const bool slow = __any_sync(0xffffffffu, S.nwf > G * WPL || Q.nwf > G * WPL);
   if (!slow) {
-    u32 xs, xq = 0;
-    const bool es = S.edge(gl, xs);
-    const bool eq = REV && Q.edge(gl, xq);
-    u8 vs = 0, vq = 0;
-    if (es) {
-      vs = d[REV ? (S.a + S.e - 1u - xs) : xs];
-      if (LUT) vs = lut[vs];
+    constexpr u32 ER = (6 + G - 1) / G;  // rounds a group needs to cover the six ragged bytes of a segment
+    u32 xs[ER], xq[ER];
+    bool es[ER], eq[ER];
+    u8 vs[ER], vq[ER];
+#pragma unroll
+    for (u32 t = 0; t < ER; t++) {
+      es[t] = S.edge(gl + t * G, xs[t]);
+      eq[t] = REV && Q.edge(gl + t * G, xq[t]);
+      vs[t] = 0;
+      vq[t] = 0;
+      if (es[t]) {
+        vs[t] = d[REV ? (S.a + S.e - 1u - xs[t]) : xs[t]];
+        if (LUT) vs[t] = lut[vs[t]];
+      }
+      if (eq[t]) vq[t] = d[Q.a + Q.e - 1u - xq[t]];
     }
-    if (eq) vq = d[Q.a + Q.e - 1u - xq];
     u32 sv[WPL], qv[WPL];
 #pragma unroll
     for (u32 j = 0; j < WPL; j++) {
@@ -158,8 +165,11 @@ __device__ __forceinline__ void record_inplace(u8 *d, u32 so, u32 sl, u32 qo, co
       if (idx < S.nwf) w32[S.wi + idx] = sv[j];
       if (REV && idx < Q.nwf) w32[Q.wi + idx] = qv[j];
     }
-    if (es) d[xs] = vs;
-    if (eq) d[xq] = vq;
+#pragma unroll
+    for (u32 t = 0; t < ER; t++) {
+      if (es[t]) d[xs[t]] = vs[t];
+      if (eq[t]) d[xq[t]] = vq[t];
+    }
     __syncwarp();
   } else {
     // long segments: independent byte pairs (i, L-1-i), no hazards
@@ -438,7 +448,9 @@ __global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs 
 
     // ---- in-place transform
     if (a.reverse || a.use_lut) {
-      if (a.group == 8) {
+      if (a.group == 4) {
+        transform_tile<C, 4, 10>(sm, d, n_own, a.reverse, a.use_lut);
+      } else if (a.group == 8) {
         if (a.wpl <= 5) transform_tile<C, 8, 5>(sm, d, n_own, a.reverse, a.use_lut);
         else transform_tile<C, 8, 8>(sm, d, n_own, a.reverse, a.use_lut);
       } else if (a.group == 16) {

@@ -144,6 +144,14 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
     }
     reset_status();
   }
+  // plain re-formatting (no reversal, no byte map, whole record): the general path compacts byte ranges
+  // (k_emit_contig) or moves 16-byte windows (k_emit), which beats assembling the tile byte by byte
+  if (!need_lut && !cfg.reverse && cfg.marker && cfg.print_seq && (!fastq || cfg.print_qual) && !o_.OnlyId &&
+      getenv("BSK_FORCE_FUSED") == nullptr) {
+    alphabet_ = saved_alpha;
+    alphabet_known_ = saved_known;
+    return kFusedFallback;
+  }
   // output can only grow through FASTA line wrapping: one '\n' per `width` bases, plus a final newline
   size_t bound = (size_t)n + 64;
   if (!fastq && cfg.width) bound += (size_t)n / cfg.width;
@@ -281,7 +289,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   // lanes per record: 8 lanes x 8 words hold segments up to ~256 B (reads), 32 x 4 up to ~512 B; longer ones take
   // the byte-pair path inside the kernel
   int group = first_seq_len_ <= 250 ? 8 : 32;
-  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : atoi(e) == 16 ? 16 : 32;
+  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 4 ? 4 : atoi(e) == 8 ? 8 : atoi(e) == 16 ? 16 : 32;
   // the newline scan first covers the halo as far as two records like the first one reach
   const u32 scan_halo = 2u * first_rec_bytes_ + 64u;
   k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group,

@@ -35,6 +35,13 @@ def main():
         "stats_fastq": ("Stats", {"Tabular": True, "All": True}, lambda: synth.fastq_reads(nbytes, seed=2), "stats", 1.0),
         "rmdup": ("RmDup", {"BySeq": True}, lambda: synth.fastq_reads(nbytes, seed=3, dup_frac=0.2), "rmdup", None),
         "translate": ("Translate", {"Frame": ["6"]}, lambda: synth.fasta_cds(nbytes, seed=5), None, None),
+        "seq_fasta_rc": ("SeqTransform", {"Reverse": True, "Complement": True}, lambda: synth.fasta_cds(nbytes, seed=5), None, None),
+        "seq_fastq_minlen": ("SeqTransform", {"MinLen": 100, "Reverse": True, "Complement": True},
+                             lambda: synth.fastq_reads(nbytes, seed=2), None, None),
+        "seq_fasta_reads": ("SeqTransform", {}, lambda: synth.fasta_reads(nbytes // 114, read_len=100, seed=1), None, None),
+        "subseq": ("SubseqTransform", {"Region": "10:-10"}, lambda: synth.fastq_reads(nbytes, seed=2), None, None),
+        "grep_id": ("Grep", {"Pattern": ["SIM:1:FC:3:2208:1391:14437"], "InvertMatch": True},
+                    lambda: synth.fastq_reads(nbytes, seed=2), None, None),
         "locate": ("Locate", {"Pattern": panel}, lambda: synth.fasta_contigs(min(nbytes, 256 << 20), seed=4), None, 1.0),
     }
     for name in args.ops.split(","):
@@ -62,6 +69,8 @@ def main():
         ms = e0.elapsed_time(e1) / args.steps
         n_rec, n_out = int(out.n_records), int(out.n)
         alg = n * alg_factor if alg_factor else n + n_out + (16 * n_rec if name == "rmdup" else 0)
+        if name == "locate":
+            alg = n  # rows are negligible
         line = {"op": name, "operator": opn, "opts": {k: (v if k != "Pattern" else "1000 x 12-mer") for k, v in opts.items()},
                 "in_bytes": n, "out_bytes": n_out, "records": n_rec, "ms_per_step": ms, "records_per_s": n_rec / ms * 1e3,
                 "gb_per_s": n / ms / 1e6, "algorithmic_bytes": alg, "whole_step_frac_of_hbm_peak": alg / ms / 1e6 / peak,
@@ -81,7 +90,8 @@ def main():
             else:
                 threads = 1
                 sb = sample.tobytes()
-                dt, _, _ = oracle.time_c_call({"translate": "orc_translate", "locate": "orc_locate"}[name], sb, opts)
+                dt, _, _ = oracle.time_c_call({"Translate": "orc_translate", "Locate": "orc_locate", "SeqTransform": "orc_seq",
+                                               "SubseqTransform": "orc_subseq", "Grep": "orc_grep"}[opn], sb, opts)
                 nr = len(oracle.frame(sb)) - 1
             line["cpu_port"] = {"records_per_s": nr / dt, "gb_per_s": sample.nbytes / dt / 1e9, "cores": threads,
                                 "sample_bytes": int(sample.nbytes)}
