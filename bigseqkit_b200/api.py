@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "bsk_version", "bsk_device_count", "bsk_create", "bsk_create_error", "bsk_destroy", "bsk_last_error",
     "bsk_set_elem_offsets", "bsk_reset", "bsk_run_buffer", "bsk_run_device", "bsk_stream", "bsk_get_timings",
     "bsk_stats_result", "bsk_stats_merge", "bsk_stats_add", "bsk_stats_dense_device", "bsk_stats_render",
-    "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
+    "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
 ]
 
 
@@ -69,6 +69,8 @@ class Library:
         L.bsk_reset.argtypes = [vp]
         L.bsk_run_buffer.argtypes = [vp, vp, sz, i64, C.POINTER(_Out)]
         L.bsk_run_device.argtypes = [vp, vp, sz, i64, C.POINTER(_Out)]
+        L.bsk_shard_bounds.argtypes = [C.c_char_p, C.c_int, C.POINTER(u64)]
+        L.bsk_run_file.argtypes = [vp, C.c_char_p, u64, u64, i64, C.c_char_p, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
         L.bsk_stream.argtypes = [vp]
         L.bsk_stream.restype = vp
         L.bsk_get_timings.argtypes = [vp, C.POINTER(_Timings)]
@@ -98,6 +100,16 @@ def default_library():
     if _default is None:
         _default = Library()
     return _default
+
+
+def shard_bounds(path, n_shards, lib=None):
+    """record-aligned byte ranges of a FASTA/FASTQ file (bsk_shard_bounds): n_shards + 1 offsets"""
+    lib = lib or default_library()
+    b = (C.c_uint64 * (n_shards + 1))()
+    rc = lib.cdll.bsk_shard_bounds(os.fsencode(path), n_shards, b)
+    if rc != BSK_OK:
+        raise BskError(rc, "bsk_shard_bounds(%s) failed" % path)
+    return list(b)
 
 
 def _as_json(opts):
@@ -183,6 +195,15 @@ class Operator:
         if out.elem_off:
             offs = list((C.c_uint64 * (out.n_elem + 1)).from_address(out.elem_off))
         return Result(d, offs, out.n_records)
+
+    def call_file(self, path, off=0, length=0, out_path=None, out_off=0, partition_id=0):
+        """Call() on the byte range [off, off+length) of a file (length 0 = to the end); the result is written to
+        out_path at out_off.  Returns (output bytes, input records, elements)."""
+        ob, nr, ne = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.cdll.bsk_run_file(self.h, os.fsencode(path), off, length, partition_id,
+                                               os.fsencode(out_path) if out_path else None, out_off, C.byref(ob), C.byref(nr),
+                                               C.byref(ne)))
+        return ob.value, nr.value, ne.value
 
     def call_device(self, dev_ptr, nbytes, partition_id=0):
         """Call() on a partition resident in HBM; returns the raw struct with DEVICE pointers."""

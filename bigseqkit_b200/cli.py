@@ -198,7 +198,7 @@ def main(argv=None):
             rows = []
             for i, f in enumerate(files):
                 with Operator("Stats", opts, device=a.device) as op:
-                    op.call(open(f, "rb").read())
+                    op.call_file(f)  # bsk_run_file: pinned staging, pipelined H2D
                     rows.append(op.stats_render("input%d" % i, "N/A"))
             out = rows[0] + "".join(r.split("\n", 1)[1] for r in rows[1:]) if a.tabular else "".join(rows)
             sys.stdout.write(out)
@@ -206,10 +206,12 @@ def main(argv=None):
         out_path = a.out_file or (files[0] + "-out" if len(files) == 1 else None)
         if out_path is None:
             raise SystemExit("out file -o required")
-        with Operator(op_name, opts, device=a.device) as op, open(out_path, "wb") as w:
+        open(out_path, "wb").close()
+        off = 0
+        with Operator(op_name, opts, device=a.device) as op:
+            op.set_elem_offsets(False)  # the merged file needs no element table
             for i, f in enumerate(files):  # every input file is one partition; outputs are appended in order
-                res = op.call(open(f, "rb").read(), partition_id=i)
-                w.write(res.data)
+                off += op.call_file(f, 0, 0, out_path, off, partition_id=i)[0]
     except BskError as e:
         sys.stderr.write("bigseqkit: %s\n" % e)
         return 1

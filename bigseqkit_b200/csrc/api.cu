@@ -4,6 +4,10 @@
 #include <string>
 
 #include "bsk.h"
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+
 #include "engine.h"
 
 struct bsk_ctx {
@@ -99,6 +103,94 @@ int bsk_run_device(bsk_ctx *ctx, const void *d_in, size_t n, int64_t partition_i
   if (!ctx || !out || (!d_in && n)) return BSK_ERR_ARG;
   ctx->eng->err.clear();
   BSK_GUARD(ctx, return ctx->eng->run_device(d_in, n, partition_id, out);)
+}
+
+// ---- file-level entry points (host code: POSIX I/O around bsk_run_buffer)
+static bool record_start_at(const std::vector<unsigned char> &w, size_t i, bool fq) {
+  // w holds bytes [base, base + w.size()); i >= 3 is an index into it
+  const unsigned char marker = fq ? '@' : '>';
+  if (w[i - 1] != '\n' || w[i] != marker) return false;
+  if (fq && w[i - 3] == '\n' && w[i - 2] == '+') return false;
+  return true;
+}
+
+int bsk_shard_bounds(const char *path, int n_shards, uint64_t *bounds) {
+  if (!path || n_shards < 1 || !bounds) return BSK_ERR_ARG;
+  FILE *f = fopen(path, "rb");
+  if (!f) return BSK_ERR_ARG;
+  fseeko(f, 0, SEEK_END);
+  const uint64_t n = (uint64_t)ftello(f);
+  int first = 0;
+  if (n) { fseeko(f, 0, SEEK_SET); first = fgetc(f); }
+  const bool fq = first == '@';
+  bounds[0] = 0;
+  std::vector<unsigned char> w;
+  for (int r = 1; r < n_shards; r++) {
+    uint64_t pos = n / (uint64_t)n_shards * (uint64_t)r;
+    if (pos < bounds[r - 1]) pos = bounds[r - 1];
+    uint64_t cut = n;
+    // scan forward in 1 MiB windows (3 bytes of look-behind) for the next record start
+    while (pos < n) {
+      const uint64_t base = pos >= 3 ? pos - 3 : 0;
+      const size_t want = (size_t)std::min<uint64_t>(n - base, (1u << 20) + 3);
+      w.resize(want);
+      fseeko(f, (off_t)base, SEEK_SET);
+      if (fread(w.data(), 1, want, f) != want) { fclose(f); return BSK_ERR_DATA; }
+      bool found = false;
+      for (size_t i = (size_t)(pos - base); i < want; i++) {
+        if (base + i == 0) { cut = 0; found = true; break; }
+        if (i >= 3 ? record_start_at(w, i, fq) : (base + i >= 1 && w[i - 1] == '\n' && w[i] == (fq ? '@' : '>'))) {
+          cut = base + i;
+          found = true;
+          break;
+        }
+      }
+      if (found) break;
+      pos = base + want;
+    }
+    bounds[r] = cut;
+  }
+  bounds[n_shards] = n;
+  fclose(f);
+  return BSK_OK;
+}
+
+int bsk_run_file(bsk_ctx *ctx, const char *path, uint64_t off, uint64_t len, int64_t partition_id, const char *out_path,
+                 uint64_t out_off, uint64_t *out_bytes, uint64_t *n_records, uint64_t *n_elem) {
+  if (!ctx || !path) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  FILE *f = fopen(path, "rb");
+  if (!f) { ctx->eng->err = std::string("cannot open ") + path; return BSK_ERR_ARG; }
+  fseeko(f, 0, SEEK_END);
+  const uint64_t fsz = (uint64_t)ftello(f);
+  if (off > fsz) off = fsz;
+  if (len == 0 || off + len > fsz) len = fsz - off;
+  int rc = BSK_OK;
+  bsk_out out;
+  memset(&out, 0, sizeof out);
+  BSK_GUARD(ctx, {
+    unsigned char *buf = ctx->eng->file_arena(len);  // pinned: the H2D copies of the pipeline are true DMA
+    fseeko(f, (off_t)off, SEEK_SET);
+    if (len && fread(buf, 1, len, f) != len) { fclose(f); ctx->eng->err = std::string("short read on ") + path; return BSK_ERR_DATA; }
+    fclose(f);
+    f = nullptr;
+    rc = ctx->eng->run_buffer(buf, len, partition_id, &out);
+  })
+  if (f) fclose(f);
+  if (rc != BSK_OK) return rc;
+  if (out_path) {
+    FILE *g = fopen(out_path, "r+b");
+    if (!g) g = fopen(out_path, "w+b");
+    if (!g) { ctx->eng->err = std::string("cannot open ") + out_path; return BSK_ERR_ARG; }
+    fseeko(g, (off_t)out_off, SEEK_SET);
+    const bool ok = out.n == 0 || fwrite(out.data, 1, out.n, g) == out.n;
+    fclose(g);
+    if (!ok) { ctx->eng->err = std::string("short write on ") + out_path; return BSK_ERR_DATA; }
+  }
+  if (out_bytes) *out_bytes = out.n;
+  if (n_records) *n_records = out.n_records;
+  if (n_elem) *n_elem = out.n_elem;
+  return BSK_OK;
 }
 
 void *bsk_stream(bsk_ctx *ctx) { return ctx ? (void *)ctx->eng->stream : nullptr; }

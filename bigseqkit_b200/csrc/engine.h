@@ -34,6 +34,8 @@ class Engine {
   int run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out);
   int run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out);
   int reset();
+  // pinned staging buffer of bsk_run_file (kept across calls)
+  u8 *file_arena(size_t n) { h_file_.reserve(n + 64); return h_file_.as<u8>(); }
 
   // stats
   int stats_result(bsk_stats *out);
@@ -87,7 +89,7 @@ class Engine {
   DevBuf b_tmp_, b_keep_, b_out_len_, b_out_off_, b_out_, b_elem_, b_id_, b_gap_seq_, b_gap_qual_, b_newlen_;
   DevBuf b_tables_, b_lens_sorted_, b_rle_u_, b_rle_c_;
   DevBuf b_op1_, b_op2_, b_op3_, b_op4_, b_op5_, b_op6_, b_op7_, b_op8_;
-  PinnedBuf h_out_, h_elem_, h_small_;
+  PinnedBuf h_out_, h_elem_, h_small_, h_file_;
   // bsk_run_buffer pipeline: second input / output buffer sets, copy streams, hand-over events
   DevBuf b_in2_, b_out2_, b_elem2_;
   cudaStream_t s_in_ = nullptr, s_out_ = nullptr;

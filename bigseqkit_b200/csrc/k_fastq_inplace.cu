@@ -64,6 +64,7 @@ typedef Cfg<512, 3, 2, 4> CfgC;   // as A with a 4-stage ring (loads issued 2.6 
 typedef Cfg<512, 3, 3, 2> CfgD;   // as A with a 2-stage ring and 3 CTAs / SM (<= 40 registers per thread)
 typedef Cfg<512, 3, 4, 2, 2048> CfgE;   // 4 CTAs / SM: 64 warps, <= 32 registers per thread, 55 KB of shared memory
 typedef Cfg<384, 4, 4, 2, 2048> CfgF;   // 4 CTAs / SM of 12 warps, <= 40 registers per thread
+typedef Cfg<448, 3, 3, 3> CfgG;         // 17 KiB tiles: 3 CTAs / SM of 14 warps with a 3-stage ring, <= 48 registers
 }  // namespace fq
 
 struct FqInplaceArgs {
@@ -532,7 +533,9 @@ __global__ void k_fastq_elem_expand(const u32 *__restrict__ tile_cnt, const u64 
   for (u32 r = lane; r < c; r += 32) elem_off[b + r] = (u64)tile * tile_bytes + slots[(size_t)tile * fq::RCAP + r];
 }
 
-u32 fastq_inplace_tile_bytes(int variant) { return variant == 1 ? fq::CfgB::T : fq::CfgA::T; }  // all others share A's tile
+u32 fastq_inplace_tile_bytes(int variant) {  // all others share A's tile
+  return variant == 1 ? fq::CfgB::T : variant == 6 ? fq::CfgG::T : fq::CfgA::T;
+}
 static_assert(fq::CfgC::T == fq::CfgA::T && fq::CfgD::T == fq::CfgA::T && fq::CfgE::T == fq::CfgA::T && fq::CfgF::T == fq::CfgA::T, "tile bytes");
 u32 fastq_inplace_tiles(u32 n, int variant) {
   const u32 t = fastq_inplace_tile_bytes(variant);
@@ -579,6 +582,7 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   else if (variant == 3) launch_fastq_inplace<fq::CfgD>(a, n_sm, s);
   else if (variant == 4) launch_fastq_inplace<fq::CfgE>(a, n_sm, s);
   else if (variant == 5) launch_fastq_inplace<fq::CfgF>(a, n_sm, s);
+  else if (variant == 6) launch_fastq_inplace<fq::CfgG>(a, n_sm, s);
   else launch_fastq_inplace<fq::CfgA>(a, n_sm, s);
 }
 

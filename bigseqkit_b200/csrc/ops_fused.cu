@@ -278,7 +278,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
     n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
   }
   int variant = 3;  // CTA shapes of k_fastq_inplace.cu (fq::CfgA..F); 3 = 512 threads x 3 CTAs / SM, 2-stage ring (measured best)
-  if (const char *e = getenv("BSK_FQ_VARIANT")) variant = atoi(e) >= 0 && atoi(e) <= 5 ? atoi(e) : 0;
+  if (const char *e = getenv("BSK_FQ_VARIANT")) variant = atoi(e) >= 0 && atoi(e) <= 6 ? atoi(e) : 0;
   const u32 n_tiles = k::fastq_inplace_tiles(n, variant);
   u8 *out = b_out_.get<u8>((size_t)n + 64);
   u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);

@@ -113,6 +113,21 @@ int bsk_run_buffer(bsk_ctx *ctx, const uint8_t *in, size_t n, int64_t partition_
 /* Same Call() on a partition already resident in HBM (d_in: device pointer,
  * n < 4 GiB - 64); out->data / out->elem_off are device pointers. */
 int bsk_run_device(bsk_ctx *ctx, const void *d_in, size_t n, int64_t partition_id, bsk_out *out);
+/* File-level entry points -- what a driver that reads files itself (the reference's ReadFASTA / ReadFASTQ + StoreFASTX,
+ * bigseqkit/helper.go:148-195, bigseqkit-lib/helper.go:378-460) calls instead of handing Go strings around.
+ *
+ * bsk_shard_bounds: cut the file into n_shards contiguous record-aligned byte ranges (every cut moves forward to the
+ *   next record start: FASTA a line starting '>', FASTQ a line starting '@' that does not follow a bare "+" line);
+ *   bounds receives n_shards + 1 offsets.  This is the job worker.PlainFile(path, delim) does for the reference.
+ * bsk_run_file: one Call() on the byte range [off, off + len) of `path` (len == 0: to the end of the file), which must
+ *   start on a record.  The range is read into pinned memory, run through the same three-stream pipeline as
+ *   bsk_run_buffer, and the result (every element followed by '\n') is written to out_path at byte offset
+ *   out_off (the file is created if needed, never truncated), so that ranks can write one merged file at the
+ *   offsets an all-gather of their sizes gave them.  out_path == NULL: nothing is written (stats).
+ *   *out_bytes / *n_records / *n_elem receive the totals when not NULL. */
+int bsk_shard_bounds(const char *path, int n_shards, uint64_t *bounds);
+int bsk_run_file(bsk_ctx *ctx, const char *path, uint64_t off, uint64_t len, int64_t partition_id, const char *out_path,
+                 uint64_t out_off, uint64_t *out_bytes, uint64_t *n_records, uint64_t *n_elem);
 /* cudaStream_t the ctx launches on (as void*), for callers that time with CUDA events. */
 void *bsk_stream(bsk_ctx *ctx);
 int bsk_get_timings(const bsk_ctx *ctx, bsk_timings *t);

@@ -214,7 +214,7 @@ def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
     assert r.data == exp[0] and list(r.elem_off) == exp[1] and t["fused_blocks"] == 1
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6"])
 @pytest.mark.parametrize("group", ["4", "8", "16", "32"])
 def test_inplace_lane_group_variants(lib, monkeypatch, group, variant):
     monkeypatch.setenv("BSK_FQ_GROUP", group)
