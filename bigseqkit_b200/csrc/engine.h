@@ -122,6 +122,8 @@ class Engine {
   int finish_grep_count(BlockOut &bo);
   int rmdup_hash_block();
   int rmdup_resolve_block(BlockOut &bo);
+  int rmdup_finish(BlockOut &bo, bool prepare_only);
+  int op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only);
 
   void free_op_state();
   void reset_op_state();

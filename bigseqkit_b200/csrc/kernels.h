@@ -119,6 +119,14 @@ u32 stats_tile_bins();
 void stats_tile(const u8 *in, u32 n, u64 *hist, DevStatus *st, int fastq, int all, int fq_offset, const u8 *gap_letters,
                 int n_gap, u32 scan_halo, int n_sm, cudaStream_t s);
 
+// ---- rmdup front half on 4-line FASTQ reads in one streaming pass (k_rmdup_tile.cu)
+u32 rmdup_tile_tiles(u32 n);
+u32 rmdup_tile_slot_stride();
+size_t rmdup_tile_slot_bytes();
+void rmdup_tile(const u8 *in, u32 n, void *slots, u32 *tile_cnt, DevStatus *st, int subject, int n_sm, cudaStream_t s);
+void rmdup_tile_compact(const void *slots, const u32 *tile_cnt, const u64 *tile_base, u32 n_tiles, u64 *keys, u64 *fps,
+                        RecArrays ra, u32 *id_len, cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

@@ -263,6 +263,11 @@ int Engine::op_rmdup(BlockOut &bo, bool prepare_only) {
   }
   rc = rmdup_hash_block();
   if (rc != BSK_OK) return rc;
+  return rmdup_finish(bo, prepare_only);
+}
+
+// keys / fingerprints of the block are in b_op1_ / b_op2_ and rm_->sv_* describes the subjects: resolve + emit
+int Engine::rmdup_finish(BlockOut &bo, bool prepare_only) {
   if (!prepare_only) return rmdup_resolve_block(bo);
   // RmDupPrepare: every record formatted, keys kept for bsk_rmdup_keys
   RmdupState *rm = rm_;
@@ -283,6 +288,95 @@ int Engine::op_rmdup(BlockOut &bo, bool prepare_only) {
   views_.name_off = ra_.head_off;
   views_.name_len = ra_.head_len;
   return emit_records(cfg, nullptr, nullptr, bo);
+}
+
+// Short 4-line FASTQ records: index + parse + hash in one streaming kernel (k_rmdup_tile.cu), then the same
+// resolve / emit as the general path.  kFusedFallback when the block is outside that grammar.
+int Engine::op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only) {
+  if (n == 0 || !fused_ok_ || o_.IgnoreCase || getenv("BSK_NO_RMDUP_TILE")) return kFusedFallback;
+  bool fastq = false, ok = false;
+  const int saved_alpha = alphabet_;
+  const bool saved_known = alphabet_known_;
+  if (!alphabet_known_ || first_block_) {
+    int rc = first_record_alphabet(d_in, n, fastq, ok);
+    if (rc != BSK_OK) return rc;
+    if (!ok || !fastq) { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; }
+  } else {
+    fastq = part_fastq_;
+    if (!fastq) return kFusedFallback;
+  }
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, device_ >= 0 ? device_ : 0));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  reset_status();
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  const u32 n_tiles = k::rmdup_tile_tiles(n);
+  void *slots = b_op3_.get<u8>((size_t)n_tiles * k::rmdup_tile_slot_stride() * k::rmdup_tile_slot_bytes());
+  u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
+  BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
+  const int subject = o_.BySeq ? 0 : (o_.ByName ? 1 : 2);
+  main_begin();
+  k::rmdup_tile(d_in, n, slots, tile_cnt, d_status_, subject, n_sm_, stream);
+  main_end();
+  launches_++;
+  u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
+  prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  u8 *hs = h_small_.as<u8>();
+  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  fetch_status();  // synchronises the stream
+  if (h_status_->counters[0] || (o_.IDNCBI && subject == 2)) {
+    alphabet_ = saved_alpha;
+    alphabet_known_ = saved_known;
+    main_timed_ = false;
+    timings.main_launches--;
+    return kFusedFallback;
+  }
+  u64 nrec;
+  memcpy(&nrec, hs, 8);
+  // the block state the general path would have left behind (no line index on this path)
+  in_ = d_in;
+  n_ = n;
+  n_rec_ = (u32)nrec;
+  n_nl_ = n_lines_ = 4 * n_rec_;
+  fastq_ = true;
+  squeezed_ = false;
+  if (first_block_) part_fastq_ = true;
+  ix_ = RecIndex{d_in, n, nullptr, nullptr, n_lines_, n_rec_, 1};
+  const size_t R = (size_t)n_rec_ + 1;
+  u32 *rec = b_rec_.get<u32>(R * 10);
+  ra_.head_off = rec;
+  ra_.head_len = rec + R;
+  ra_.seq_line0 = rec + 2 * R;
+  ra_.seq_line1 = rec + 3 * R;
+  ra_.seq_off = rec + 4 * R;
+  ra_.seq_len = rec + 5 * R;
+  ra_.qual_line0 = rec + 6 * R;
+  ra_.qual_line1 = rec + 7 * R;
+  ra_.qual_off = rec + 8 * R;
+  ra_.qual_len = rec + 9 * R;
+  BSK_CUDA(cudaMemsetAsync(ra_.seq_len + n_rec_, 0, 4, stream));
+  BSK_CUDA(cudaMemsetAsync(ra_.qual_len + n_rec_, 0, 4, stream));
+  u64 *keys = b_op1_.get<u64>(R);
+  u64 *fps = b_op2_.get<u64>(R);
+  u32 *ids = b_id_.get<u32>(R * 2);
+  k::rmdup_tile_compact(slots, tile_cnt, tile_base, n_tiles, keys, fps, ra_, ids + R, stream);
+  launches_++;
+  seq_space_ = qual_space_ = n;
+  set_views_default();
+  bo.n_rec = n_rec_;
+  if (n_rec_) any_record_ = true;
+  if (first_block_) {  // a new partition: forget the previous one
+    if (rm_) rmdup_state_reset(rm_);
+    rmdup_removed = 0;
+  }
+  if (!rm_) rm_ = new RmdupState();
+  rm_->sv_base = d_in;
+  rm_->sv_off = subject == 0 ? ra_.seq_off : ra_.head_off;
+  rm_->sv_len = subject == 0 ? ra_.seq_len : (subject == 1 ? ra_.head_len : ids + R);
+  timings.fused_blocks++;
+  return rmdup_finish(bo, prepare_only);
 }
 
 int Engine::rmdup_keys(const int64_t **keys, size_t *n) {

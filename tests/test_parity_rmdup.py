@@ -110,3 +110,35 @@ def test_rmdup_compacts_byte_ranges_like_the_formatter(lib, monkeypatch):
         got2 = run_lib(lib, "RmDup", data, {"BySeq": True})
         monkeypatch.delenv("BSK_NO_CONTIG")
         assert got2[0] == exp[0] and list(got2[1]) == list(exp[1]), name
+
+
+@pytest.mark.parametrize("opts", [{"BySeq": True}, {"ByName": True}, {}], ids=["by_seq", "by_name", "by_id"])
+def test_rmdup_tile_front_end_matches_general_path(lib, monkeypatch, opts):
+    # k_rmdup_tile (index + parse + hash in one pass) against the four-pass general path and the oracle
+    from bigseqkit_b200 import synth
+    from test_fused_path import _fixed_fastq
+    reads = synth.fastq_reads(150 << 10, seed=83, dup_frac=0.3).tobytes()
+    same_ids = b"".join(b"@id%d desc %d\nACGT%s\n+\nIIII%s\n" % (i % 97, i, b"A" * (100 + i % 50), b"I" * (100 + i % 50)) for i in range(1500))
+    for name, data in (("reads", reads), ("repeated_ids", same_ids), ("rec128_tile_aligned", _fixed_fastq(1500, 8, 57, 84) * 2)):
+        exp = run_oracle("RmDup", data, opts)
+        with Operator("RmDup", opts, lib=lib) as o:
+            r = o.call(data)
+            t = o.timings()
+            keys = o.rmdup_keys()
+        assert r.data == exp[0] and list(r.elem_off) == list(exp[1]), (name, opts)
+        assert t["fused_blocks"] == 1, (name, t)
+        monkeypatch.setenv("BSK_NO_RMDUP_TILE", "1")
+        with Operator("RmDup", opts, lib=lib) as o:
+            r2 = o.call(data)
+            assert o.timings()["fused_blocks"] == 0
+            keys2 = o.rmdup_keys()
+        monkeypatch.delenv("BSK_NO_RMDUP_TILE")
+        assert r2.data == exp[0] and keys == keys2, (name, opts)
+    # outside the tile grammar: "+name" lines, FASTA, --ignore-case -> general path, same answers
+    for data, o2 in ((_fixed_fastq(300, 9, 80, 85, plus="x"), opts), (synth.fasta_reads(800, read_len=60, seed=86).tobytes() * 2, opts),
+                     (reads, dict(opts, IgnoreCase=True))):
+        exp = run_oracle("RmDup", data, o2)
+        with Operator("RmDup", o2, lib=lib) as o:
+            r = o.call(data)
+            assert o.timings()["fused_blocks"] == 0
+        assert r.data == exp[0]
