@@ -104,8 +104,70 @@ void Engine::set_views_default() {
   views_.n_rec = n_rec_;
 }
 
+// 4-line FASTQ reads: record index + parse in ONE streaming pass (k_rmdup_tile.cu without the hashing) instead of
+// count + fill + parse.  kFusedFallback when the block is outside that grammar (the general passes below then run).
+int Engine::prepare_block_tile(const u8 *d_in, u32 n) {
+  if (n == 0 || !fused_ok_ || getenv("BSK_NO_TILE_INDEX")) return kFusedFallback;
+  u8 *hs = h_small_.as<u8>();
+  BSK_CUDA(cudaMemcpyAsync(hs, d_in, 1, cudaMemcpyDeviceToHost, stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  if (hs[0] != '@') return kFusedFallback;
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, device_ >= 0 ? device_ : 0));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  reset_status();
+  if (first_block_) upload_tables();
+  const u32 n_tiles = k::rmdup_tile_tiles(n);
+  void *slots = b_op3_.get<u8>((size_t)n_tiles * k::rmdup_tile_slot_stride() * k::rmdup_tile_slot_bytes());
+  u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
+  BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
+  k::rmdup_tile(d_in, n, slots, tile_cnt, d_status_, -1, n_sm_, stream);
+  launches_++;
+  u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
+  prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  fetch_status();  // synchronises the stream
+  if (h_status_->counters[0]) return kFusedFallback;
+  u64 nrec;
+  memcpy(&nrec, hs, 8);
+  in_ = d_in;
+  n_ = n;
+  n_rec_ = (u32)nrec;
+  n_nl_ = n_lines_ = 4 * n_rec_;
+  fastq_ = true;
+  squeezed_ = false;
+  if (first_block_) part_fastq_ = true;
+  ix_ = RecIndex{d_in, n, nullptr, nullptr, n_lines_, n_rec_, 1};
+  const size_t R = (size_t)n_rec_ + 1;
+  u32 *rec = b_rec_.get<u32>(R * 10);
+  ra_.head_off = rec;
+  ra_.head_len = rec + R;
+  ra_.seq_line0 = rec + 2 * R;
+  ra_.seq_line1 = rec + 3 * R;
+  ra_.seq_off = rec + 4 * R;
+  ra_.seq_len = rec + 5 * R;
+  ra_.qual_line0 = rec + 6 * R;
+  ra_.qual_line1 = rec + 7 * R;
+  ra_.qual_off = rec + 8 * R;
+  ra_.qual_len = rec + 9 * R;
+  BSK_CUDA(cudaMemsetAsync(ra_.seq_len + n_rec_, 0, 4, stream));
+  BSK_CUDA(cudaMemsetAsync(ra_.qual_len + n_rec_, 0, 4, stream));
+  k::rmdup_tile_compact(slots, tile_cnt, tile_base, n_tiles, nullptr, nullptr, ra_, nullptr, stream);
+  launches_++;
+  seq_space_ = qual_space_ = n;
+  set_views_default();
+  h_status_->counters[0] = 0;
+  return BSK_OK;
+}
+
 // index + parse + squeeze.  Leaves errors (if any) in h_status_ for check_errors().
 int Engine::prepare_block(const u8 *d_in, u32 n) {
+  {
+    const int trc = prepare_block_tile(d_in, n);
+    if (trc != kFusedFallback) return trc;
+  }
   in_ = d_in;
   n_ = n;
   n_nl_ = n_rec_ = n_lines_ = 0;

@@ -130,6 +130,7 @@ class Engine {
   void reset_status();
   void fetch_status();
   int prepare_block(const u8 *d_in, u32 n);
+  int prepare_block_tile(const u8 *d_in, u32 n);
   int resolve_alphabet();
   int check_errors();
   std::string describe_error(u64 rec, u32 kind);

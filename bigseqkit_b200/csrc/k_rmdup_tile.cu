@@ -48,7 +48,7 @@ struct RmdupTileArgs {
   u32 *tile_cnt;       // [n_tiles + 1]
   DevStatus *st;       // counters[0] = declined tiles
   u32 n_tiles;
-  int subject;         // 0 sequence, 1 name, 2 id
+  int subject;         // 0 sequence, 1 name, 2 id; -1: index + parse only (no hashing)
 };
 
 // 8 / 4 little-endian bytes at region offset off + i from aligned 32-bit words (reads up to 3 bytes of slack)
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(rt::G::NT, rt::G::CTAS) k_rmdup_tile(RmdupTile
         u32 so = l1, slen = sl;
         if (a.subject == 1) { so = p0 + 1; slen = hl; }
         else if (a.subject == 2) { so = p0 + 1; slen = idl; }
-        u64 ka, kb2;
-        xxh64_pair(GetWords{d, so}, slen, 0, kSeedB, ka, kb2, true);
+        u64 ka = 0, kb2 = 0;
+        if (a.subject >= 0) xxh64_pair(GetWords{d, so}, slen, 0, kSeedB, ka, kb2, true);
         RmdupSlot sl_;
         sl_.key = ka;
         sl_.fp = kb2;
@@ -219,8 +219,10 @@ __global__ void k_rmdup_tile_compact(const RmdupSlot *__restrict__ slots, const 
   for (u32 r = lane; r < c; r += 32) {
     const RmdupSlot s = slots[(size_t)tile * rt::RCAP + r];
     const u64 i = b + r;
-    keys[i] = s.key;
-    fps[i] = s.fp;
+    if (keys) {
+      keys[i] = s.key;
+      fps[i] = s.fp;
+    }
     const u32 ho = s.rec_start + 1, so = ho + s.hl + 1;
     ra.head_off[i] = ho;
     ra.head_len[i] = s.hl;
@@ -229,7 +231,7 @@ __global__ void k_rmdup_tile_compact(const RmdupSlot *__restrict__ slots, const 
     ra.qual_off[i] = so + s.sl + 3;
     ra.qual_len[i] = s.sl;
     ra.seq_line0[i] = ra.seq_line1[i] = ra.qual_line0[i] = ra.qual_line1[i] = 0;  // no line index on this path
-    id_len[i] = s.idl;
+    if (id_len) id_len[i] = s.idl;
   }
 }
 
