@@ -157,16 +157,20 @@ __device__ __forceinline__ void merge16(u32 w[4], const u32 ww[4], u32 shift, u3
 // source buffer, or a run that needs the byte path (reversed and / or mapped sequence).
 struct Piece {
   u32 len;        // bytes in the piece from p on (>= 1)
-  int kind;       // 0 literal, 1 straight copy, 2 byte path
+  int kind;       // 0 literal, 1 run of source bytes
   u8 lit;
-  const u8 *base; // kind 1: source buffer and offset of the first byte
+  const u8 *base; // kind 1: source buffer and offset of the byte that comes out FIRST
   u64 src;
+  bool rev;       // kind 1: the following output bytes come from DEcreasing source offsets
+  bool map;       // kind 1: bytes go through the sequence byte map
 };
 
-__device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, const RecOut &o, u32 p, bool seq_plain) {
+__device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, const RecOut &o, u32 p, bool has_lut) {
   Piece pc;
   pc.base = nullptr;
   pc.src = 0;
+  pc.rev = false;
+  pc.map = false;
   if (p < o.np) {
     u32 q = p;
     if (c.marker) {
@@ -189,8 +193,11 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
       if (run > o.seq_len - j) run = o.seq_len - j;
     }
     pc.len = run;
-    if (seq_plain) { pc.kind = 1; pc.base = v.seqb; pc.src = (u64)o.seq_off + j; }
-    else pc.kind = 2;
+    pc.kind = 1;
+    pc.base = v.seqb;
+    pc.map = has_lut;
+    pc.rev = c.reverse != 0;
+    pc.src = c.reverse ? (u64)o.seq_off + (o.seq_len - 1u - j) : (u64)o.seq_off + j;
     return pc;
   }
   p -= o.ns;
@@ -201,23 +208,25 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
   }
   if (p < o.qual_len) {
     pc.len = o.qual_len - p;
-    if (!c.reverse) { pc.kind = 1; pc.base = v.qualb; pc.src = (u64)o.qual_off + p; }
-    else pc.kind = 2;
+    pc.kind = 1;
+    pc.base = v.qualb;
+    pc.rev = c.reverse != 0;
+    pc.src = c.reverse ? (u64)o.qual_off + (o.qual_len - 1u - p) : (u64)o.qual_off + p;
     return pc;
   }
   pc.kind = 0; pc.len = 1; pc.lit = '\n';
   return pc;
 }
 
-// One aligned 16-byte store per thread and step.  Runs that are plain copies of source bytes (names, unreversed
-// sequence / quality lines, translated proteins) move as 16-byte windows; only reversed or mapped sequence bytes
-// and single literal bytes are assembled byte by byte.
+// One aligned 16-byte store per thread and step.  Every run of source bytes (names, sequence / quality lines in
+// either direction, translated proteins) moves as a 16-byte window -- byte-reversed with four PRMT for --reverse,
+// mapped through the 256-byte table for --complement / case / dna2rna; only the literal bytes are placed one by one.
 __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
                                               u64 total, const u8 *__restrict__ lut, u64 in_limit, u64 seq_limit, u64 qual_limit) {
   __shared__ u32 s_r[2];
   const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
   cta_record_range(off, v.n_rec, o0, total, s_r);
-  const bool seq_plain = !c.reverse && lut == nullptr;
+  const bool has_lut = lut != nullptr;
   for (u32 ch = 0; ch < kEmitChunks; ch++) {
     const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
     if (o >= total) return;
@@ -237,19 +246,41 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
         ro = load_rec(v, c, r);
         p = 0;
       }
-      const Piece pc = piece_at(v, c, ro, p, seq_plain);
+      const Piece pc = piece_at(v, c, ro, p, has_lut);
       u32 cnt = pc.len;
       if (cnt > oend - pos) cnt = (u32)(oend - pos);
       const u32 shift = (u32)(pos - o);
       if (pc.kind == 0) {
         w[shift >> 2] |= (u32)pc.lit << (8 * (shift & 3));
-      } else if (pc.kind == 1 && pc.src >= shift) {
-        u32 ww[4];
-        const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
-        window16(pc.base, pc.src - shift, limit, ww);
-        merge16(w, ww, shift, cnt);
       } else {
-        for (u32 t = 0; t < cnt; t++) w[(shift + t) >> 2] |= (u32)rec_byte(v, c, ro, p + t, lut) << (8 * ((shift + t) & 3));
+        // Window of 16 source bytes laid out so that chunk byte shift+t holds the t-th byte of the run: forward runs
+        // start the window at src - shift; reversed runs end it at src + shift and are byte-reversed after the load.
+        const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
+        const bool fits = pc.rev ? (pc.src + shift >= 15) : (pc.src >= shift);
+        if (fits) {
+          u32 ww[4];
+          if (!pc.rev) {
+            window16(pc.base, pc.src - shift, limit, ww);
+          } else {
+            u32 t4[4];
+            window16(pc.base, pc.src + shift - 15, limit, t4);
+            ww[0] = __byte_perm(t4[3], 0, 0x0123);
+            ww[1] = __byte_perm(t4[2], 0, 0x0123);
+            ww[2] = __byte_perm(t4[1], 0, 0x0123);
+            ww[3] = __byte_perm(t4[0], 0, 0x0123);
+          }
+          if (pc.map) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const u32 x = ww[q];
+              ww[q] = (u32)lut[x & 0xffu] | ((u32)lut[(x >> 8) & 0xffu] << 8) | ((u32)lut[(x >> 16) & 0xffu] << 16) |
+                      ((u32)lut[x >> 24] << 24);
+            }
+          }
+          merge16(w, ww, shift, cnt);
+        } else {
+          for (u32 t = 0; t < cnt; t++) w[(shift + t) >> 2] |= (u32)rec_byte(v, c, ro, p + t, lut) << (8 * ((shift + t) & 3));
+        }
       }
       pos += cnt;
       p += cnt;

@@ -61,7 +61,8 @@ __device__ __forceinline__ u32 tr_warp_search(const u64 *__restrict__ off, u32 n
 
 __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u64 *__restrict__ poff, u64 total,
                                                    const u8 *__restrict__ code_fwd, const u8 *__restrict__ code_rev,
-                                                   const u8 *__restrict__ lut, u8 *__restrict__ prot, DevStatus *st) {
+                                                   const u8 *__restrict__ lut, u8 *__restrict__ prot, DevStatus *st,
+                                                   u64 seq_limit) {
   __shared__ u8 s_fwd[256], s_rev[256], s_lut[4096];
   __shared__ u32 s_e[2];
   s_fwd[threadIdx.x] = code_fwd[threadIdx.x];
@@ -94,7 +95,59 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
   u32 start = (u32)((f < 0 ? -f : f) - 1), l = v.seq_len[r];
   const u8 *s = v.seqb + v.seq_off[r];
   u32 w[4] = {0, 0, 0, 0};
+  // Fast path: all 16 amino acids belong to this element and their 48 nucleotides can be fetched as three 16-byte
+  // windows (five aligned word loads + funnel shifts each) instead of 48 byte loads.
+  const u32 i0 = start + 3u * j;  // first nucleotide index (on the translated strand)
+  bool fast = a0 + kTrAA <= eend && a0 + kTrAA <= total && i0 + 48u <= l;
+  u64 lo_addr = 0;
+  if (fast) {
+    const u64 sbase = (u64)v.seq_off[r];
+    lo_addr = f > 0 ? sbase + i0 : sbase + (l - 48u - i0);  // lowest source byte of the 48
+    fast = (lo_addr & ~3ull) + 52 <= seq_limit;            // whole words stay inside the readable buffer
+  }
+  if (fast) {
+    u32 nt[12];
+    {
+      const u32 *wp = reinterpret_cast<const u32 *>(v.seqb + (lo_addr & ~3ull));
+      const u32 sh = (u32)(lo_addr & 3ull) * 8u;
+      u32 x[13];
 #pragma unroll
+      for (int q = 0; q < 13; q++) x[q] = wp[q];
+#pragma unroll
+      for (int q = 0; q < 12; q++) nt[q] = __funnelshift_r(x[q], x[q + 1], sh);
+    }
+#pragma unroll
+    for (int t = 0; t < (int)kTrAA; t++) {
+      u32 c0, c1, c2;
+      if (f > 0) {
+        c0 = s_fwd[(nt[(3 * t) >> 2] >> (8 * ((3 * t) & 3))) & 0xffu];
+        c1 = s_fwd[(nt[(3 * t + 1) >> 2] >> (8 * ((3 * t + 1) & 3))) & 0xffu];
+        c2 = s_fwd[(nt[(3 * t + 2) >> 2] >> (8 * ((3 * t + 2) & 3))) & 0xffu];
+      } else {  // codon t reads the window from its top: bytes 47-3t, 46-3t, 45-3t
+        c0 = s_rev[(nt[(47 - 3 * t) >> 2] >> (8 * ((47 - 3 * t) & 3))) & 0xffu];
+        c1 = s_rev[(nt[(46 - 3 * t) >> 2] >> (8 * ((46 - 3 * t) & 3))) & 0xffu];
+        c2 = s_rev[(nt[(45 - 3 * t) >> 2] >> (8 * ((45 - 3 * t) & 3))) & 0xffu];
+      }
+      u8 aa;
+      bool init = false;
+      if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
+      else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
+        aa = 'X';
+        if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
+      } else {
+        const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
+        aa = x & 0x7f;
+        init = (x & 0x80) != 0;
+      }
+      if (c.init_m && j + (u32)t == 0 && init) aa = 'M';
+      if (c.clean && aa == '*') aa = 'X';
+      w[t >> 2] |= (u32)aa << (8 * (t & 3));
+    }
+    *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
+    return;
+  }
+  // slow path: element boundaries inside the 16 amino acids, or the last codons of a sequence
+#pragma unroll 1
   for (int t = 0; t < (int)kTrAA; t++) {
     const u64 a = a0 + (u64)t;
     if (a < total) {
@@ -134,14 +187,9 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
       }
       if (c.init_m && j == 0 && init) aa = 'M';
       if (c.clean && aa == '*') aa = 'X';
-      w[t >> 2] |= (u32)aa << (8 * (t & 3));
+      prot[a] = aa;  // rare path: plain byte stores keep w[] in registers for the fast path
       j++;
     }
-  }
-  if (a0 + kTrAA <= total) {
-    *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
-  } else {
-    for (u32 t = 0; a0 + t < total; t++) prot[a0 + t] = (u8)(w[t >> 2] >> (8 * (t & 3)));
   }
 }
 
@@ -281,7 +329,7 @@ int Engine::op_translate(BlockOut &bo) {
   if (ptotal) {
     main_begin();
     BSK_LAUNCH(k_translate, (u32)((ptotal + 256ull * kTrAA - 1) / (256ull * kTrAA)), 256, 0, stream, views_, c, poff, ptotal,
-               d_tab, d_tab + 256, d_tab + 512, prot, d_status_);
+               d_tab, d_tab + 256, d_tab + 512, prot, d_status_, views_.seqb == in_ ? (u64)n_ : ~0ull);
     main_end();
     launches_++;
     fetch_status();
