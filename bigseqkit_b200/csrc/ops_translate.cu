@@ -23,21 +23,23 @@ struct TrCfg {
 };
 
 // untrimmed protein length per (record, frame); records shorter than 3 nt are an error
-__global__ void k_tr_len(RecViews v, TrCfg c, u32 *__restrict__ plen, DevStatus *st) {
+__global__ void k_tr_len(RecViews v, TrCfg c, u32 *__restrict__ plen, u32 *__restrict__ ppad, DevStatus *st) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 n_el = v.n_rec * c.nf;
   if (e > n_el) return;
-  if (e == n_el) { plen[e] = 0; return; }
+  if (e == n_el) { plen[e] = 0; ppad[e] = 0; return; }
   const u32 r = e / c.nf, fi = e - r * c.nf;
   const u32 l = v.seq_len[r];
   if (l < 3) {
     plen[e] = 0;
+    ppad[e] = 0;
     atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_TOO_SHORT);
     return;
   }
   const int f = c.frames[fi];
   const u32 start = (u32)((f < 0 ? -f : f) - 1);
   plen[e] = (l - start) / 3;
+  ppad[e] = ((l - start) / 3 + 15u) & ~15u;  // arena slots are padded to 16 amino acids: one element per 16-byte chunk
 }
 
 // One thread per 16 consecutive amino acids of the arena (one aligned 16-byte store); the CTA finds the range of
@@ -62,7 +64,7 @@ __device__ __forceinline__ u32 tr_warp_search(const u64 *__restrict__ off, u32 n
 __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u64 *__restrict__ poff, u64 total,
                                                    const u8 *__restrict__ code_fwd, const u8 *__restrict__ code_rev,
                                                    const u8 *__restrict__ lut, u8 *__restrict__ prot, DevStatus *st,
-                                                   u64 seq_limit) {
+                                                   u64 seq_limit, const u32 *__restrict__ plen) {
   __shared__ u8 s_fwd[256], s_rev[256], s_lut[4096];
   __shared__ u32 s_e[2];
   s_fwd[threadIdx.x] = code_fwd[threadIdx.x];
@@ -87,23 +89,24 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
     else hi = mid;
   }
   u32 e = lo;
-  u64 eend = poff[e + 1];
-  u32 j = (u32)(a0 - poff[e]);
-  // element state, refreshed whenever the arena position crosses into the next (record, frame)
-  u32 r = e / c.nf;
-  int f = c.frames[e - r * c.nf];
-  u32 start = (u32)((f < 0 ? -f : f) - 1), l = v.seq_len[r];
+  const u32 j = (u32)(a0 - poff[e]);  // slots are padded to 16: the whole chunk belongs to element e
+  const u32 r = e / c.nf;
+  const int f = c.frames[e - r * c.nf];
+  const u32 start = (u32)((f < 0 ? -f : f) - 1), l = v.seq_len[r];
   const u8 *s = v.seqb + v.seq_off[r];
   u32 w[4] = {0, 0, 0, 0};
   // Fast path: all 16 amino acids belong to this element and their 48 nucleotides can be fetched as three 16-byte
   // windows (five aligned word loads + funnel shifts each) instead of 48 byte loads.
   const u32 i0 = start + 3u * j;  // first nucleotide index (on the translated strand)
-  bool fast = a0 + kTrAA <= eend && a0 + kTrAA <= total && i0 + 48u <= l;
+  const u32 valid = plen[e] - j;  // amino acids of this chunk that exist (>= 1); the rest of the slot is padding
+  // the 48-byte window may run past the end of the sequence (forward frames) or below its start (reverse frames):
+  // it only has to stay inside the buffer
+  const u64 sbase = (u64)v.seq_off[r];
+  bool fast = f > 0 ? true : sbase + l >= 48ull + i0;
   u64 lo_addr = 0;
   if (fast) {
-    const u64 sbase = (u64)v.seq_off[r];
-    lo_addr = f > 0 ? sbase + i0 : sbase + (l - 48u - i0);  // lowest source byte of the 48
-    fast = (lo_addr & ~3ull) + 52 <= seq_limit;            // whole words stay inside the readable buffer
+    lo_addr = f > 0 ? sbase + i0 : sbase + l - 48u - i0;  // lowest source byte of the 48
+    fast = (lo_addr & ~3ull) + 52 <= seq_limit;          // whole words stay inside the readable buffer
   }
   if (fast) {
     u32 nt[12];
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
       if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
       else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
         aa = 'X';
-        if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
+        if (!c.allow_unknown && (u32)t < valid)
+          atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
       } else {
         const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
         aa = x & 0x7f;
@@ -146,62 +150,47 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
     *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
     return;
   }
-  // slow path: element boundaries inside the 16 amino acids, or the last codons of a sequence
+  // slow path (window would leave the buffer: first / last records of a block): byte loads, valid codons only
 #pragma unroll 1
-  for (int t = 0; t < (int)kTrAA; t++) {
-    const u64 a = a0 + (u64)t;
-    if (a < total) {
-      if (a >= eend) {
-        do {
-          e++;
-          eend = poff[e + 1];
-        } while (a >= eend);
-        j = 0;
-        r = e / c.nf;
-        f = c.frames[e - r * c.nf];
-        start = (u32)((f < 0 ? -f : f) - 1);
-        l = v.seq_len[r];
-        s = v.seqb + v.seq_off[r];
-      }
-      const u32 i = start + 3u * j;
-      u32 c0, c1, c2;
-      if (f > 0) {
-        c0 = s_fwd[s[i]];
-        c1 = s_fwd[s[i + 1]];
-        c2 = s_fwd[s[i + 2]];
-      } else {  // codon i of the reverse complement
-        c0 = s_rev[s[l - 1 - i]];
-        c1 = s_rev[s[l - 2 - i]];
-        c2 = s_rev[s[l - 3 - i]];
-      }
-      u8 aa;
-      bool init = false;
-      if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
-      else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
-        aa = 'X';
-        if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
-      } else {
-        const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
-        aa = x & 0x7f;
-        init = (x & 0x80) != 0;
-      }
-      if (c.init_m && j == 0 && init) aa = 'M';
-      if (c.clean && aa == '*') aa = 'X';
-      prot[a] = aa;  // rare path: plain byte stores keep w[] in registers for the fast path
-      j++;
+  for (u32 t = 0; t < valid && t < kTrAA; t++) {
+    const u32 i = i0 + 3u * t;
+    u32 c0, c1, c2;
+    if (f > 0) {
+      c0 = s_fwd[s[i]];
+      c1 = s_fwd[s[i + 1]];
+      c2 = s_fwd[s[i + 2]];
+    } else {  // codon i of the reverse complement
+      c0 = s_rev[s[l - 1 - i]];
+      c1 = s_rev[s[l - 2 - i]];
+      c2 = s_rev[s[l - 3 - i]];
     }
+    u8 aa;
+    bool init = false;
+    if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
+    else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
+      aa = 'X';
+      if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
+    } else {
+      const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
+      aa = x & 0x7f;
+      init = (x & 0x80) != 0;
+    }
+    if (c.init_m && j + t == 0 && init) aa = 'M';
+    if (c.clean && aa == '*') aa = 'X';
+    prot[a0 + t] = aa;
   }
 }
 
 // --trim + the element views handed to the record formatter
-__global__ void k_tr_views(RecViews v, TrCfg c, const u64 *__restrict__ poff, const u8 *__restrict__ prot,
+__global__ void k_tr_views(RecViews v, TrCfg c, const u64 *__restrict__ poff, const u32 *__restrict__ plen,
+                           const u8 *__restrict__ prot,
                            const u32 *__restrict__ hdr_off, const u32 *__restrict__ hdr_len, u32 *name_off, u32 *name_len,
                            u32 *seq_off, u32 *seq_len) {
   const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
   const u32 n_el = v.n_rec * c.nf;
   if (e >= n_el) return;
   const u32 r = e / c.nf;
-  u32 pl = (u32)(poff[e + 1] - poff[e]);
+  u32 pl = plen[e];  // poff[] holds the padded slots
   const u8 *p = prot + poff[e];
   if (c.trim)
     while (pl && (p[pl - 1] == 'X' || p[pl - 1] == '*')) pl--;
@@ -315,9 +304,10 @@ int Engine::op_translate(BlockOut &bo) {
 
   u32 *plen = b_op2_.get<u32>((size_t)n_el + 1);
   u64 *poff = b_op3_.get<u64>((size_t)n_el + 1);
-  BSK_LAUNCH_FLAT(k_tr_len, (n_el + 1 + 255) / 256, 256, 0, stream, views_, c, plen, d_status_);
+  u32 *ppad = b_op8_.get<u32>((size_t)n_el + 1);
+  BSK_LAUNCH_FLAT(k_tr_len, (n_el + 1 + 255) / 256, 256, 0, stream, views_, c, plen, ppad, d_status_);
   launches_++;
-  prim::excl_scan_u32_to_u64(plen, poff, (size_t)n_el + 1, b_tmp_, stream);
+  prim::excl_scan_u32_to_u64(ppad, poff, (size_t)n_el + 1, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>() + 8192;
   BSK_CUDA(cudaMemcpyAsync(hs, poff + n_el, 8, cudaMemcpyDeviceToHost, stream));
   fetch_status();  // also syncs the copy above; errors are judged after the codon pass (earliest record wins)
@@ -329,7 +319,7 @@ int Engine::op_translate(BlockOut &bo) {
   if (ptotal) {
     main_begin();
     BSK_LAUNCH(k_translate, (u32)((ptotal + 256ull * kTrAA - 1) / (256ull * kTrAA)), 256, 0, stream, views_, c, poff, ptotal,
-               d_tab, d_tab + 256, d_tab + 512, prot, d_status_, views_.seqb == in_ ? (u64)n_ : ~0ull);
+               d_tab, d_tab + 256, d_tab + 512, prot, d_status_, views_.seqb == in_ ? (u64)n_ : ~0ull, plen);
     main_end();
     launches_++;
     fetch_status();
@@ -361,7 +351,7 @@ int Engine::op_translate(BlockOut &bo) {
   }
   u32 *ev = b_op7_.get<u32>(((size_t)n_el + 1) * 4);
   const size_t E = (size_t)n_el + 1;
-  BSK_LAUNCH_FLAT(k_tr_views, (n_el + 255) / 256, 256, 0, stream, views_, c, poff, prot, hdr_off, hdr_len, ev, ev + E,
+  BSK_LAUNCH_FLAT(k_tr_views, (n_el + 255) / 256, 256, 0, stream, views_, c, poff, plen, prot, hdr_off, hdr_len, ev, ev + E,
                   ev + 2 * E, ev + 3 * E);
   launches_++;
   RecViews saved = views_;
