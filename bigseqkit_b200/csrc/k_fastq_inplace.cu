@@ -523,14 +523,22 @@ __global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs 
   if (tid == 0) tma::bulk_wait_all();
 }
 
-// element offsets from the per-tile slot lists: one warp per tile
+// element offsets from the per-tile slot lists: one warp per tile.  Launched before the host knows the record
+// count: writes are bounded by `cap` entries (the host re-runs it with a larger array in the rare overflow case),
+// and the terminating entry elem_off[n_records] = total output bytes comes from the main kernel's status word.
 __global__ void k_fastq_elem_expand(const u32 *__restrict__ tile_cnt, const u64 *__restrict__ tile_base,
-                                    const u16 *__restrict__ slots, u64 *__restrict__ elem_off, u32 n_tiles, u32 tile_bytes) {
+                                    const u16 *__restrict__ slots, u64 *__restrict__ elem_off, u32 n_tiles, u32 tile_bytes,
+                                    u64 cap, const DevStatus *__restrict__ st) {
   const u32 tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   const u32 c = tile_cnt[tile];
   const u64 b = tile_base[tile];
-  for (u32 r = lane; r < c; r += 32) elem_off[b + r] = (u64)tile * tile_bytes + slots[(size_t)tile * fq::RCAP + r];
+  for (u32 r = lane; r < c; r += 32)
+    if (b + r < cap) elem_off[b + r] = (u64)tile * tile_bytes + slots[(size_t)tile * fq::RCAP + r];
+  if (tile == n_tiles - 1 && lane == 0) {
+    const u64 nrec = tile_base[n_tiles];
+    if (nrec < cap) elem_off[nrec] = st->counters[1];
+  }
 }
 
 u32 fastq_inplace_tile_bytes(int variant) {  // all others share A's tile
@@ -587,11 +595,11 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
 }
 
 void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
-                       cudaStream_t s) {
+                       u64 cap, const DevStatus *st, cudaStream_t s) {
   if (!n_tiles) return;
   const u64 threads = (u64)n_tiles * 32;
   BSK_LAUNCH_FLAT(k_fastq_elem_expand, (u32)((threads + 255) / 256), 256, 0, s, tile_cnt, tile_base, slots, elem_off, n_tiles,
-                  fastq_inplace_tile_bytes(variant));
+                  fastq_inplace_tile_bytes(variant), cap, st);
 }
 
 }  // namespace k

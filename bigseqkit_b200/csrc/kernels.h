@@ -112,7 +112,7 @@ u32 fastq_inplace_slot_stride();
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
                    int use_lut, int group, u32 max_seg, u32 scan_halo, int variant, int n_sm, cudaStream_t s);
 void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
-                       cudaStream_t s);
+                       u64 cap, const DevStatus *st, cudaStream_t s);
 
 // ---- stats on short records in one streaming pass (k_stats_tile.cu)
 u32 stats_tile_bins();

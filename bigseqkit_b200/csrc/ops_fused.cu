@@ -298,6 +298,17 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   launches_++;
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
   prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  // element offsets are expanded before the host knows the record count (one host round trip instead of two): the
+  // array is sized from the partition's first record, with a re-run in the rare case that was too small
+  u64 *elem = nullptr;
+  u64 cap = 0;
+  if (want_elem_off) {
+    cap = (u64)n / (first_rec_bytes_ > 16 ? first_rec_bytes_ / 2 : 8) + 1024;
+    if (b_elem_.cap / 8 > cap) cap = b_elem_.cap / 8;
+    elem = b_elem_.get<u64>((size_t)cap);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, cap, d_status_, stream);
+    launches_++;
+  }
   u8 *hs = h_small_.as<u8>();
   BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
   fetch_status();  // synchronises the stream
@@ -315,13 +326,11 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   u64 nrec;
   memcpy(&nrec, hs, 8);
   const u64 total = h_status_->counters[1];
-  u64 *elem = nullptr;
-  if (want_elem_off) {
-    elem = b_elem_.get<u64>((size_t)nrec + 2);
-    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, stream);
+  if (want_elem_off && nrec + 1 > cap) {  // more records than the first one suggested
+    cap = nrec + 2;
+    elem = b_elem_.get<u64>((size_t)cap);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, cap, d_status_, stream);
     launches_++;
-    memcpy(hs + 16, &total, 8);
-    BSK_CUDA(cudaMemcpyAsync(elem + nrec, hs + 16, 8, cudaMemcpyHostToDevice, stream));
   }
   fastq_ = fastq;
   if (first_block_) part_fastq_ = fastq;

@@ -155,6 +155,8 @@ def inplace_inputs():
         "qual_starts_with_at_and_plus": b"@r\nACGT\n+\n@+@+\n@s\nGG\n+\n+@\n" * 250,
         # short first record (small first-attempt scan halo), then records that end far into the halo: rescan path
         "short_then_long": _fixed_fastq(1, 4, 20, 27) + _fixed_fastq(120, 10, 900, 28) + _fixed_fastq(40, 10, 1700, 29),
+        # long first record, then many short ones: more elements than the first record suggests (offset array re-run)
+        "long_then_short": _fixed_fastq(1, 10, 900, 44) + _fixed_fastq(4000, 6, 40, 45),
         "tiny_file": b"@a\nACGT\n+\nIIII\n",
         "tiny_file_no_nl": b"@a\nAC\n+\nII",
     }
@@ -167,7 +169,8 @@ def test_inplace_parity(lib, opts):
         r, t = run(lib, data, opts)
         assert r.data == exp[0], (name, opts)
         assert list(r.elem_off) == exp[1], (name, opts)
-        assert t["fused_blocks"] == 1 and t["kernel_launches"] == 2, (name, opts, t)
+        # main kernel + offset expansion (+ one re-run of the expansion when the first record under-estimates the count)
+        assert t["fused_blocks"] == 1 and t["kernel_launches"] == (3 if name == "long_then_short" else 2), (name, opts, t)
 
 
 INPLACE_OUTSIDE_GRAMMAR = {
