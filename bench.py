@@ -23,6 +23,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 OPTS = {"Reverse": True, "Complement": True}
+# measured DRAM traffic of k_fastq_inplace per launch by block size in MiB (ncu, see profiles/); algorithmic = 2 * block
+NCU_DRAM_TRAFFIC = {1024: 1078597120 + 1037827584}
 METRIC = "fastq_records_per_sec"
 
 
@@ -289,7 +291,10 @@ def main_ours(args):
             "config": config(args, n, n_rec), "gb_per_s": bytes_all * args.steps / (ms_max * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": ("k_fastq_inplace (TMA-staged tile kernel: newline scan + record grammar + in-place revcomp, bulk store)"
                                                     if fused else "k_emit (general path record formatter)"),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_TRAFFIC.get(args.block_mib) if fused else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture in "
+                                           "profiles/r1_ncu_dram_traffic_k_fastq_inplace_1GiB.csv (same block size)",
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": main_per, "peak_source": peak_src,
                          "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
                          "stage_ms": {"index": index_ms / args.steps, "op": op_ms / args.steps}},
