@@ -220,6 +220,10 @@ def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
 @pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6"])
 @pytest.mark.parametrize("group", ["4", "8", "16", "32"])
 def test_inplace_lane_group_variants(lib, monkeypatch, group, variant):
+    # every combination runs on the GPU; the host emulator (slow: OS threads) takes a covering subset
+    if lib.path.endswith("libbsk_emu.so") and (group, variant) not in {("8", "3"), ("4", "0"), ("16", "1"), ("32", "2"), ("8", "4"),
+                                                                      ("16", "5"), ("32", "6")}:
+        pytest.skip("covered on the GPU")
     monkeypatch.setenv("BSK_FQ_GROUP", group)
     monkeypatch.setenv("BSK_FQ_VARIANT", variant)
     opts = {"Reverse": True, "Complement": True}
