@@ -109,17 +109,6 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   emu::sync_warp();
   return r;
 }
-static inline unsigned __match_any_sync(unsigned, unsigned v) {
-  uint64_t *s = emu::wslots();
-  int lane = threadIdx.x & 31;
-  s[lane] = v;
-  emu::sync_warp();
-  unsigned r = 0;
-  for (int i = 0; i < 32; i++)
-    if ((unsigned)s[i] == v) r |= 1u << i;
-  emu::sync_warp();
-  return r;
-}
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, p) == 0xffffffffu; }
 static inline unsigned __activemask() { return 0xffffffffu; }

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
       return r;
     };
     // a complete owned record: length -> histogram; with -a its sequence / quality lines -> work items
-    // (the histogram is bumped once per warp and distinct length, see hist_add below)
     auto commit = [&](u32 k, const Ev &r) {
+      atomicAdd(&sm.hist[r.slen], 1u);
       if (!a.all || !r.slen) return;
       if (fq) {
         const u32 i0 = atomicAdd(&sm.n_item, 2u);
@@ -153,14 +153,6 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
           }
         } else sm.bad = 1;
       }
-    };
-
-    // one shared-memory atomic per warp and distinct length: read sets have one length, so a plain atomicAdd per
-    // record would serialise the whole CTA on a single histogram bin.  Every lane of the warp must call it.
-    auto hist_add = [&](bool valid, u32 slen) {
-      const u32 key = valid ? slen : 0xffffffffu;
-      const u32 peers = __match_any_sync(0xffffffffu, key);
-      if (valid && lane == (u32)__ffs((int)peers) - 1u) atomicAdd(&sm.hist[slen], (u32)__popc(peers));
     };
 
     u32 hs = a.scan_halo;
@@ -188,7 +180,6 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
           else if (r.st == 2) sm.bad = 1;
           else if (direct) commit(kb + tid, r);
         }
-        if (direct) hist_add(r.own && r.st == 0, r.slen);
         if (!direct) mine = r;
         const u32 bal = __ballot_sync(0xffffffffu, r.own && r.st == 0);
         n_new += (u32)__popc(bal);
@@ -201,10 +192,7 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
         __syncthreads();  // everybody has read the flags before thread 0 clears them again
         continue;
       }
-      if (!direct) {
-        if (mine.own) commit(tid, mine);
-        hist_add(mine.own && mine.st == 0, mine.slen);
-      }
+      if (!direct && mine.own) commit(tid, mine);
       if (lane == 0 && n_new) atomicAdd(&sm.n_rec, n_new);
       if (!direct) {
         __syncthreads();  // work items pushed by commit()
