@@ -555,10 +555,13 @@ template <class C>
 static void launch_fastq_inplace(FqInplaceArgs a, int n_sm, cudaStream_t s) {
   const size_t smem = sizeof(typename C::Smem) + 16;
 #ifndef BSK_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_fastq_inplace<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   u32 grid = (u32)n_sm * C::CTAS;

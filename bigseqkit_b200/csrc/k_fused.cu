@@ -496,10 +496,13 @@ void seq_fused(const u8 *in, u32 n, u8 *out, u64 *elem_off, const u8 *lut, void 
   a.max_len = max_len;
   const u32 n_tiles = (n + FT - 1) / FT;
 #ifndef BSK_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_seq_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes());
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   BSK_LAUNCH(k_seq_fused, n_tiles, FTHREADS, fused_smem_bytes(), s, a);

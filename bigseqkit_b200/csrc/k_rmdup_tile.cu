@@ -250,10 +250,13 @@ void rmdup_tile(const u8 *in, u32 n, void *slots, u32 *tile_cnt, DevStatus *st, 
   a.subject = subject;
   const size_t smem = sizeof(rt::Smem) + 16;
 #ifndef BSK_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_rmdup_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   u32 grid = (u32)n_sm * rt::G::CTAS;

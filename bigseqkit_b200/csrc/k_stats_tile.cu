@@ -294,10 +294,13 @@ void stats_tile(const u8 *in, u32 n, u64 *hist, DevStatus *st, int fastq, int al
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > tile::H ? tile::H : scan_halo);
   const size_t smem = sizeof(st::Smem) + 16;
 #ifndef BSK_EMU
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(k_stats_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev] = true;
   }
 #endif
   u32 grid = (u32)n_sm * st::G::CTAS;
