@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "bsk_version", "bsk_device_count", "bsk_create", "bsk_create_error", "bsk_destroy", "bsk_last_error",
     "bsk_set_elem_offsets", "bsk_reset", "bsk_run_buffer", "bsk_run_device", "bsk_stream", "bsk_get_timings",
     "bsk_stats_result", "bsk_stats_merge", "bsk_stats_add", "bsk_stats_dense_device", "bsk_stats_render",
-    "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
+    "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_dup_seqs", "bsk_rmdup_dup_num", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
 ]
 
 
@@ -82,6 +82,8 @@ class Library:
         L.bsk_stats_render.restype = C.c_long
         L.bsk_rmdup_keys.argtypes = [vp, C.POINTER(C.POINTER(i64)), C.POINTER(sz)]
         L.bsk_rmdup_removed.argtypes = [vp]
+        for f in ("bsk_rmdup_dup_seqs", "bsk_rmdup_dup_num"):
+            getattr(L, f).argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(sz)]
         L.bsk_rmdup_removed.restype = u64
         L.bsk_rmdup_prepare_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(u64)]
         L.bsk_rmdup_resolve_device.argtypes = [vp, vp, u64, C.POINTER(_Out)]
@@ -260,6 +262,20 @@ class Operator:
 
     def rmdup_removed(self):
         return self.lib.cdll.bsk_rmdup_removed(self.h)
+
+    def _rmdup_text(self, fn):
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        self._check(getattr(self.lib.cdll, fn)(self.h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value) if n.value else b""
+
+    def rmdup_dup_seqs(self):
+        """-d: removed records (bigseqkit-lib/rmdup.go:185-187), accumulated since the partition started."""
+        return self._rmdup_text("bsk_rmdup_dup_seqs")
+
+    def rmdup_dup_num(self):
+        """-D: "count\tid1, id2, ..." rows (bigseqkit-lib/rmdup.go:230-234)."""
+        return self._rmdup_text("bsk_rmdup_dup_num")
 
     def rmdup_prepare_device(self, dev_ptr, nbytes, fp_ptr, fp_cap):
         nrec = C.c_uint64(0)

@@ -212,6 +212,12 @@ def main(argv=None):
             op.set_elem_offsets(False)  # the merged file needs no element table
             for i, f in enumerate(files):  # every input file is one partition; outputs are appended in order
                 off += op.call_file(f, 0, 0, out_path, off, partition_id=i)[0]
+                if a.cmd == "rmdup":  # written per input like After does per executor (bigseqkit-lib/rmdup.go:245-275)
+                    mode = "wb" if i == 0 else "ab"
+                    if a.dup_seqs_file:
+                        open(a.dup_seqs_file, mode).write(op.rmdup_dup_seqs())
+                    if a.dup_num_file:
+                        open(a.dup_num_file, mode).write(op.rmdup_dup_num())
     except BskError as e:
         sys.stderr.write("bigseqkit: %s\n" % e)
         return 1

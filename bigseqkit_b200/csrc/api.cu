@@ -237,6 +237,16 @@ int bsk_rmdup_keys(bsk_ctx *ctx, const int64_t **keys, size_t *n) {
   BSK_GUARD(ctx, return ctx->eng->rmdup_keys(keys, n);)
 }
 
+int bsk_rmdup_dup_seqs(bsk_ctx *ctx, const char **data, size_t *n) {
+  if (!ctx || !data || !n) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->rmdup_dup_seqs(data, n);)
+}
+
+int bsk_rmdup_dup_num(bsk_ctx *ctx, const char **data, size_t *n) {
+  if (!ctx || !data || !n) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, return ctx->eng->rmdup_dup_num(data, n);)
+}
+
 uint64_t bsk_rmdup_removed(const bsk_ctx *ctx) { return ctx ? ctx->eng->rmdup_removed : 0; }
 
 int bsk_rmdup_prepare_device(bsk_ctx *ctx, const void *d_in, size_t n, void *d_fp, size_t fp_cap, uint64_t *n_records) {

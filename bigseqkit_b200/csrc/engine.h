@@ -48,6 +48,8 @@ class Engine {
   int rmdup_keys(const int64_t **keys, size_t *n);
   int rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records);
   int rmdup_resolve_device(const void *d_all_fp, u64 n_before, bsk_out *out);
+  int rmdup_dup_seqs(const char **data, size_t *n);
+  int rmdup_dup_num(const char **data, size_t *n);
 
   struct RmdupState;   // ops_rmdup.cu: key table + fingerprint history of the running partition
   struct PatternSet;   // ops_match.cu: needles of locate / grep on the device
@@ -123,6 +125,7 @@ class Engine {
   int rmdup_hash_block();
   int rmdup_resolve_block(BlockOut &bo);
   int rmdup_finish(BlockOut &bo, bool prepare_only);
+  int rmdup_side_outputs(const u8 *keep, const u64 *first, u64 g_base);
   int op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only);
 
   void free_op_state();

@@ -1,6 +1,7 @@
 // op_state.h -- operator state that outlives one block (rmdup history + table, pattern tables).
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "engine.h"
@@ -19,6 +20,12 @@ struct Engine::RmdupState {
   const u8 *sv_base = nullptr;
   const u32 *sv_off = nullptr, *sv_len = nullptr;
   bool block_ready = false;
+  // rmdup -d / -D, accumulated on the host between Before and After (bigseqkit-lib/rmdup.go:102-103,224-238)
+  std::string dup_seqs;                        // removed records, Record.Format(LineWidth), input order
+  std::string id_text;                         // "ID\n" of every record seen (-D only)
+  std::vector<u64> id_off;                     // record ordinal -> offset into id_text
+  std::vector<std::pair<u64, u64>> dup_pairs;  // {ordinal of the group's first member, ordinal of the removed record}
+  std::string dup_num;                         // rendered rows
 };
 
 // Needles of locate / grep -s: every pattern on the '+' strand and, unless only the positive

@@ -4,6 +4,7 @@
 //   GroupByKey          bigseqkit/rmdup.go:97           -> one device hash table  key -> earliest record
 //   RmDupCheck.Call     bigseqkit-lib/rmdup.go:118-242  exact-subject compare inside an equal-key group, first wins
 // Pinned semantics: the first occurrence in input order survives, output in input order.
+#include <algorithm>
 #include <cstring>
 
 #include "engine.h"
@@ -87,7 +88,8 @@ __device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32
 // keep[r]: 1 first occurrence, 0 duplicate, 2 unresolved (64-bit key collision between different subjects)
 __global__ void k_rmdup_resolve(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *__restrict__ keys,
                                 const u64 *__restrict__ fps, u64 g_base, const u64 *__restrict__ hist_fp, u64 *tkeys,
-                                const u64 *__restrict__ tfirst, u64 cap, u8 *__restrict__ keep, DevStatus *st) {
+                                const u64 *__restrict__ tfirst, u64 cap, u8 *__restrict__ keep, u64 *__restrict__ first_out,
+                                DevStatus *st) {
   const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rec) return;
   const u64 g = g_base + r;
@@ -98,20 +100,30 @@ __global__ void k_rmdup_resolve(SubjectViews sv, u32 n_rec, int ignore_case, con
   else if (first >= g_base) k = subject_equal(sv, r, (u32)(first - g_base), ignore_case) ? 0 : 2;
   else k = (hist_fp[first] == fps[r]) ? 0 : 2;  // earlier block / other GPU: second 64-bit hash decides
   keep[r] = k;
+  if (first_out) first_out[r] = first;  // ordinal of the group's first member (rmdup -D)
   if (k == 2) atomicAdd((unsigned long long *)&st->counters[4], 1ull);
 }
 
 // rare path: serial scan for the records whose key collided with a different subject
 __global__ void k_rmdup_fixup(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *keys, const u64 *fps, u64 g_base,
-                              const u64 *hist_keys, const u64 *hist_fp, u8 *keep) {
+                              const u64 *hist_keys, const u64 *hist_fp, u8 *keep, u64 *first_out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (u32 r = 0; r < n_rec; r++) {
     if (keep[r] != 2) continue;
+    u64 first = g_base + r;
     bool dup = false;
-    for (u64 h = 0; h < g_base && !dup; h++) dup = hist_keys[h] == keys[r] && hist_fp[h] == fps[r];
-    for (u32 q = 0; q < r && !dup; q++) dup = keys[q] == keys[r] && subject_equal(sv, r, q, ignore_case);
+    for (u64 h = 0; h < g_base && !dup; h++)
+      if (hist_keys[h] == keys[r] && hist_fp[h] == fps[r]) { dup = true; first = h; }
+    for (u32 q = 0; q < r && !dup; q++)
+      if (keys[q] == keys[r] && subject_equal(sv, r, q, ignore_case)) { dup = true; first = g_base + q; }
     keep[r] = dup ? 0 : 1;
+    if (first_out) first_out[r] = first;
   }
+}
+
+__global__ void k_rmdup_drop_mask(const u8 *__restrict__ keep, u32 n_rec, u8 *__restrict__ drop) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rec) drop[r] = keep[r] == 0;
 }
 
 __global__ void k_interleave_fp(const u64 *keys, const u64 *fps, u64 n, u64 *out) {
@@ -182,6 +194,11 @@ void rmdup_state_free(Engine::RmdupState *rm) {
 void rmdup_state_reset(Engine::RmdupState *rm) {
   if (!rm) return;
   rm->n_hist = 0;
+  rm->dup_seqs.clear();
+  rm->id_text.clear();
+  rm->id_off.clear();
+  rm->dup_pairs.clear();
+  rm->dup_num.clear();
   rm->dirty = true;  // the table is cleared (not freed) before its next use
   rm->block_ready = false;
 }
@@ -220,23 +237,29 @@ int Engine::rmdup_resolve_block(BlockOut &bo) {
   u64 *keys = b_op1_.as<u64>(), *fps = b_op2_.as<u64>();
   SubjectViews sv{rm->sv_base, rm->sv_off, rm->sv_len};
   u8 *keep = b_keep_.get<u8>((size_t)n_rec_ + 1);
+  const bool want_dup_seqs = !o_.DupSeqsFile.empty(), want_dup_num = !o_.DupNumFile.empty();
+  u64 *first = want_dup_num ? b_op5_.get<u64>((size_t)n_rec_ + 1) : nullptr;
   if (n_rec_) {
     table_reserve(rm, g_base + n_rec_, stream, launches_);
     BSK_LAUNCH_FLAT(k_table_insert, (n_rec_ + 255) / 256, 256, 0, stream, keys, (u64)n_rec_, g_base, rm->tkeys, rm->tfirst,
                     rm->cap);
     BSK_LAUNCH_FLAT(k_rmdup_resolve, (n_rec_ + 255) / 256, 256, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps,
-                    g_base, rm->hist_fp, rm->tkeys, rm->tfirst, rm->cap, keep, d_status_);
+                    g_base, rm->hist_fp, rm->tkeys, rm->tfirst, rm->cap, keep, first, d_status_);
     launches_ += 2;
     fetch_status();
     if (h_status_->counters[4]) {
       BSK_LAUNCH_FLAT(k_rmdup_fixup, 1, 1, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps, g_base, rm->hist_keys,
-                      rm->hist_fp, keep);
+                      rm->hist_fp, keep, first);
       launches_++;
     }
     hist_reserve(rm, g_base + n_rec_, stream);
     BSK_CUDA(cudaMemcpyAsync(rm->hist_keys + g_base, keys, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
     BSK_CUDA(cudaMemcpyAsync(rm->hist_fp + g_base, fps, (size_t)n_rec_ * 8, cudaMemcpyDeviceToDevice, stream));
     rm->n_hist = g_base + n_rec_;
+  }
+  if (n_rec_ && (want_dup_seqs || want_dup_num)) {
+    int rc = rmdup_side_outputs(keep, first, g_base);
+    if (rc != BSK_OK) return rc;
   }
   // Record.Format(LineWidth) minus the final '\n' (rmdup.go:214-215) + FileStore's '\n'
   EmitCfg cfg;
@@ -252,6 +275,122 @@ int Engine::rmdup_resolve_block(BlockOut &bo) {
   int rc = emit_records(cfg, n_rec_ ? keep : nullptr, nullptr, bo);
   if (rc == BSK_OK) rmdup_removed += n_rec_ - bo.n_elem;
   return rc;
+}
+
+// rmdup -d / -D (RmDupCheck.Call bigseqkit-lib/rmdup.go:180-239): the removed records as Record.Format(LineWidth) and,
+// per record, {group's first ordinal, ID}.  Both are accumulated on the host like the reference's this.dups /
+// this.data until bsk_rmdup_dup_seqs / bsk_rmdup_dup_num fetch them (After, rmdup.go:245-275).  Runs before the
+// survivors are emitted: it borrows the output buffers.
+int Engine::rmdup_side_outputs(const u8 *keep, const u64 *first, u64 g_base) {
+  RmdupState *rm = rm_;
+  const size_t R = (size_t)n_rec_ + 1;
+  const int saved_elem = want_elem_off;
+  want_elem_off = 0;
+  int rc = BSK_OK;
+  if (!o_.DupSeqsFile.empty()) {
+    u8 *drop = b_op4_.get<u8>(R);
+    BSK_LAUNCH_FLAT(k_rmdup_drop_mask, (n_rec_ + 255) / 256, 256, 0, stream, keep, n_rec_, drop);
+    launches_++;
+    EmitCfg cfg;
+    cfg.marker = fastq_ ? '@' : '>';
+    cfg.print_name = 1;
+    cfg.print_seq = 1;
+    cfg.print_qual = fastq_;
+    cfg.plus_line = fastq_;
+    cfg.reverse = 0;
+    cfg.width = fastq_ ? 0 : (o_.LineWidth > 0 ? (u32)o_.LineWidth : 0);
+    views_.name_off = ra_.head_off;
+    views_.name_len = ra_.head_len;
+    BlockOut side;
+    rc = emit_records(cfg, drop, nullptr, side);
+    if (rc == BSK_OK && side.n) {
+      const size_t at = rm->dup_seqs.size();
+      rm->dup_seqs.resize(at + side.n);
+      BSK_CUDA(cudaMemcpyAsync(&rm->dup_seqs[at], side.d_data, side.n, cudaMemcpyDeviceToHost, stream));
+      BSK_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
+  if (rc == BSK_OK && !o_.DupNumFile.empty()) {
+    u32 *ids = b_op6_.get<u32>(R * 2);
+    views_.name_off = ra_.head_off;
+    views_.name_len = ra_.head_len;
+    k::id_desc(views_, o_.IDNCBI ? 1 : 0, ids, ids + R, nullptr, nullptr, stream);
+    launches_++;
+    views_.name_off = ids;
+    views_.name_len = ids + R;
+    EmitCfg cfg{};
+    cfg.print_name = 1;  // one "ID\n" per record
+    BlockOut side;
+    rc = emit_records(cfg, nullptr, nullptr, side);
+    views_.name_off = ra_.head_off;
+    views_.name_len = ra_.head_len;
+    if (rc == BSK_OK) {
+      const size_t at = rm->id_text.size();
+      rm->id_text.resize(at + side.n);
+      std::vector<u8> hk(n_rec_);
+      std::vector<u64> hf(n_rec_);
+      if (side.n) BSK_CUDA(cudaMemcpyAsync(&rm->id_text[at], side.d_data, side.n, cudaMemcpyDeviceToHost, stream));
+      BSK_CUDA(cudaMemcpyAsync(hk.data(), keep, n_rec_, cudaMemcpyDeviceToHost, stream));
+      BSK_CUDA(cudaMemcpyAsync(hf.data(), first, (size_t)n_rec_ * 8, cudaMemcpyDeviceToHost, stream));
+      BSK_CUDA(cudaStreamSynchronize(stream));
+      size_t pos = at;
+      for (u32 r = 0; r < n_rec_; r++) {
+        rm->id_off.push_back(pos);
+        const void *nl = memchr(rm->id_text.data() + pos, '\n', rm->id_text.size() - pos);
+        pos = nl ? (size_t)((const char *)nl - rm->id_text.data()) + 1 : rm->id_text.size();
+        if (hk[r] == 0) rm->dup_pairs.emplace_back(hf[r], g_base + r);
+      }
+    }
+  }
+  want_elem_off = saved_elem;
+  return rc;
+}
+
+int Engine::rmdup_dup_seqs(const char **data, size_t *n) {
+  if (op_ != OP_RMDUP) { err = "bsk_rmdup_dup_seqs: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
+  *data = rm_ ? rm_->dup_seqs.data() : "";
+  *n = rm_ ? rm_->dup_seqs.size() : 0;
+  return BSK_OK;
+}
+
+// rows "count\tid1, id2, ...\n" (rmdup.go:230-234), one per subject with more than one member, in the order of the
+// groups' first members; ids in input order
+int Engine::rmdup_dup_num(const char **data, size_t *n) {
+  if (op_ != OP_RMDUP) { err = "bsk_rmdup_dup_num: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
+  *data = "";
+  *n = 0;
+  if (!rm_) return BSK_OK;
+  RmdupState *rm = rm_;
+  std::stable_sort(rm->dup_pairs.begin(), rm->dup_pairs.end(),
+                   [](const std::pair<u64, u64> &a, const std::pair<u64, u64> &b) { return a.first < b.first; });
+  auto id_of = [&](u64 g, const char *&p, size_t &l) {
+    p = rm->id_text.data() + rm->id_off[g];
+    const size_t end = g + 1 < rm->id_off.size() ? rm->id_off[g + 1] : rm->id_text.size();
+    l = end - rm->id_off[g] - 1;
+  };
+  std::string &out = rm->dup_num;
+  out.clear();
+  for (size_t i = 0; i < rm->dup_pairs.size();) {
+    size_t j = i;
+    while (j < rm->dup_pairs.size() && rm->dup_pairs[j].first == rm->dup_pairs[i].first) j++;
+    if (rm->dup_pairs[i].first >= rm->id_off.size()) { err = "bsk_rmdup_dup_num: first member of a group is outside this ctx"; return BSK_ERR_STATE; }
+    out += std::to_string(j - i + 1);
+    out += '\t';
+    const char *p;
+    size_t l;
+    id_of(rm->dup_pairs[i].first, p, l);
+    out.append(p, l);
+    for (size_t k = i; k < j; k++) {
+      id_of(rm->dup_pairs[k].second, p, l);
+      out += ", ";
+      out.append(p, l);
+    }
+    out += '\n';
+    i = j;
+  }
+  *data = out.data();
+  *n = out.size();
+  return BSK_OK;
 }
 
 int Engine::op_rmdup(BlockOut &bo, bool prepare_only) {
@@ -395,6 +534,10 @@ int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t 
   if (op_ != OP_RMDUP) { err = "bsk_rmdup_prepare_device: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
   if (n >= kMaxBlockBytes) { err = "bsk_rmdup_prepare_device: shard must be smaller than 4 GiB - 1 MiB"; return BSK_ERR_ARG; }
   if (((uintptr_t)d_in & 15) != 0) { err = "bsk_rmdup_prepare_device: device pointer must be 16-byte aligned"; return BSK_ERR_ARG; }
+  if (!o_.DupNumFile.empty()) {  // the first member of a group may live on another rank
+    err = "-D/--dup-num-file needs the whole input in one ctx (bsk_run_buffer / bsk_run_file), not the sharded path";
+    return BSK_ERR_UNSUPPORTED;
+  }
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
   launches_ = 0;
   timings = bsk_timings{};

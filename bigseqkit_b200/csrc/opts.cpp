@@ -282,11 +282,6 @@ bool parse_and_validate(Op op, const char *json, Opts &o, std::string &err, int 
     case OP_RMDUP_PREPARE:  // bigseqkit/rmdup.go:79-85
       if (o.BySeq && o.ByName) { err = "only one/none of the flags -s (--by-seq) and -n (--by-name) is allowed"; return false; }
       if (o.OnlyPositiveStrand && !o.BySeq) { err = "flag -s (--by-seq) needed when using -P (--only-positive-strand)"; return false; }
-      if (!o.DupSeqsFile.empty() || !o.DupNumFile.empty()) {
-        code = BSK_ERR_UNSUPPORTED;
-        err = "-d/--dup-seqs-file and -D/--dup-num-file are outside the accelerated path";
-        return false;
-      }
       break;
     case OP_TRANSLATE: {  // bigseqkit-lib/translate.go:43-61
       if (!find_gcode(o.TranslTable)) {

@@ -20,7 +20,12 @@ import "C"
 
 import (
 	"fmt"
+	"os"
+	"path"
+	"strconv"
 	"unsafe"
+
+	"bigseqkit"
 
 	"ignis/executor/api"
 	"ignis/executor/api/base"
@@ -214,11 +219,51 @@ func NewRmDupPrepare() any { return &RmDup{} }
 
 type RmDup struct {
 	base.IMapPartitions[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *RmDup) Before(context api.IContext) error { return t.op.before(context, "RmDup") }
 func (t *RmDup) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(0, it, context)
+}
+
+// After writes the -d / -D files per executor like bigseqkit-lib/rmdup.go:245-275 (flag meaning, not the
+// directory swap of :246-267): <DupSeqsFile>/<executor id> and <DupNumFile>/<executor id>, the texts of the
+// executor's ctxs one after the other.
+func (t *RmDup) After(context api.IContext) error {
+	opts := bigseqkit.StringToOptions[bigseqkit.RmDupOptions](context.Vars()["opts"].(string))
+	write := func(dir string, numbers bool) error {
+		if len(dir) == 0 {
+			return nil
+		}
+		var text []byte
+		for _, c := range t.op.ctxs {
+			var p *C.char
+			var n C.size_t
+			var rc C.int
+			if numbers {
+				rc = C.bsk_rmdup_dup_num(c, &p, &n)
+			} else {
+				rc = C.bsk_rmdup_dup_seqs(c, &p, &n)
+			}
+			if rc != C.BSK_OK {
+				return fmt.Errorf("%s", C.GoString(C.bsk_last_error(c)))
+			}
+			text = append(text, C.GoBytes(unsafe.Pointer(p), C.int(n))...)
+		}
+		if len(text) == 0 {
+			return nil
+		}
+		if err := os.MkdirAll(dir, os.ModePerm); err != nil {
+			return err
+		}
+		return os.WriteFile(path.Join(dir, strconv.Itoa(context.ExecutorId())), text, 0o644)
+	}
+	if err := write(*opts.DupSeqsFile, false); err != nil {
+		return err
+	}
+	if err := write(*opts.DupNumFile, true); err != nil {
+		return err
+	}
+	return t.op.after()
 }

@@ -152,6 +152,15 @@ long bsk_stats_render(bsk_ctx *ctx, const char *file, const char *format, char *
 int bsk_rmdup_keys(bsk_ctx *ctx, const int64_t **keys, size_t *n);
 /* number of records dropped as duplicates by the last "RmDup" call */
 uint64_t bsk_rmdup_removed(const bsk_ctx *ctx);
+/* rmdup -d / -D (options "DupSeqsFile" / "DupNumFile" non-empty; RmDupCheck.Call bigseqkit-lib/rmdup.go:180-239,
+ * written by After :245-275).  Text accumulated over the bsk_run_* calls since the last partition start, owned by
+ * the ctx until the next call on it:
+ *   dup_seqs  every removed record as Record.Format(LineWidth), input order;
+ *   dup_num   "count\tid1, id2, ...\n" per subject with more than one member, rows ordered by the group's first
+ *             member (the reference walks a Go map there), ids in input order.
+ * The caller writes the files; the flag meaning is implemented, not the directory swap of rmdup.go:246-267. */
+int bsk_rmdup_dup_seqs(bsk_ctx *ctx, const char **data, size_t *n);
+int bsk_rmdup_dup_num(bsk_ctx *ctx, const char **data, size_t *n);
 /* Multi-GPU rmdup (the GroupByKey exchange of bigseqkit/rmdup.go:97 as one all-gather):
  *  1. bsk_rmdup_prepare_device: index + hash the local shard; d_fp receives n_records
  *     16-byte fingerprints {xxh64 seed 0, xxh64 seed 0x9E3779B97F4A7C15 ^ len};

@@ -758,6 +758,64 @@ int orc_rmdup(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out, ui
   return rc < 0 ? -1 : 0;
 }
 
+/* rmdup -d / -D side outputs (lib/rmdup.go:180-239, After :245-275).  SURVEY Q4/Q6: first occurrence in input
+ * order is the group's kept member; dup_seqs = every removed record as Record.Format(LineWidth), input order;
+ * dup_num = one row "count\tid1, id2, ..." per subject with more than one member, rows in order of the group's
+ * first member (the reference iterates a Go map there: order unspecified), ids in input order. */
+typedef struct { uint64_t key; size_t off, len, grp; } dg_ent;
+typedef struct { uint64_t count; buf_t ids; } dg_grp;
+int orc_rmdup_dups(const uint8_t *data, size_t n, const orc_opts *o, orc_out *dup_seqs, orc_out *dup_num) {
+  memset(dup_seqs, 0, sizeof *dup_seqs); memset(dup_num, 0, sizeof *dup_num);
+  if (rmdup_check_flags(o, dup_seqs->err)) return -1;
+  int ab = ab_from_type(o->SeqType, dup_seqs->err);
+  if (ab < 0) return -1;
+  parser_t p; parser_init(&p, data, n, ab, o);
+  sink_t s_seq, s_num; memset(&s_seq, 0, sizeof s_seq); memset(&s_num, 0, sizeof s_num);
+  buf_t ob, tmp, arena; memset(&ob, 0, sizeof ob); memset(&tmp, 0, sizeof tmp); memset(&arena, 0, sizeof arena);
+  size_t cap = 64; while (cap < 2 * p.n_rec + 2) cap *= 2;
+  dg_ent *tab = (dg_ent *)calloc(cap, sizeof(dg_ent));
+  dg_grp *grp = (dg_grp *)calloc(p.n_rec + 1, sizeof(dg_grp));
+  size_t n_grp = 0; int rc;
+  while ((rc = parser_read(&p)) > 0) {
+    rec_t *r = &p.r;
+    const uint8_t *s; size_t l;
+    rmdup_subject(o, r, &tmp, &s, &l);
+    uint64_t key = orc_xxh64(s, l, 0);
+    size_t i = (size_t)(key & (cap - 1));
+    int dup = 0;
+    for (;;) {
+      if (tab[i].len == 0) break;
+      if (tab[i].key == key && tab[i].len - 1 == l && memcmp(arena.p + tab[i].off, s, l) == 0) { dup = 1; break; }
+      i = (i + 1) & (cap - 1);
+    }
+    if (dup) {
+      dg_grp *g = &grp[tab[i].grp];
+      g->count++;
+      buf_add(&g->ids, (const uint8_t *)", ", 2); buf_add(&g->ids, r->id, r->id_len);       /* :188-190 */
+      int fq = p.is_fastq;
+      format_record(&ob, r->head, r->head_len, r->seq, r->seq_len, r->qual, r->qual_len, fq, fq ? 0 : o->LineWidth);
+      sink_elem(&s_seq, ob.p, ob.n - 1);                                                      /* :185-187 */
+      continue;
+    }
+    tab[i].key = key; tab[i].off = arena.n; tab[i].len = l + 1; tab[i].grp = n_grp;
+    buf_add(&arena, s, l);
+    grp[n_grp].count = 1; buf_add(&grp[n_grp].ids, r->id, r->id_len);                         /* :217-219 */
+    n_grp++;
+  }
+  for (size_t g = 0; g < n_grp; g++) {
+    if (grp[g].count > 1) {                                                                   /* :230-234 */
+      char num[32]; int k = snprintf(num, sizeof num, "%llu\t", (unsigned long long)grp[g].count);
+      ob.n = 0; buf_add(&ob, (const uint8_t *)num, (size_t)k); buf_add(&ob, grp[g].ids.p, grp[g].ids.n);
+      sink_elem(&s_num, ob.p, ob.n);
+    }
+    free(grp[g].ids.p);
+  }
+  if (rc < 0) snprintf(dup_seqs->err, 512, "%s", p.err);
+  sink_to_out(&s_seq, dup_seqs); sink_to_out(&s_num, dup_num);
+  free(tab); free(grp); free(ob.p); free(tmp.p); free(arena.p); parser_free(&p);
+  return rc < 0 ? -1 : 0;
+}
+
 /* --------------------------------------------------------------- translate
  * seq.CodonTables / Seq.Translate (UNVERIFIED bio v0.7.0 seq/codon_table.go;
  * NCBI gc.prt strings, base order TCAG) + Translate.Call (lib/translate.go:66-145)

@@ -91,6 +91,8 @@ void orc_stats_finalise(orc_stats *s, int all);
 /* renders StatsString (drv/stats.go:168-288); returns malloc'd NUL-terminated string */
 char *orc_stats_render(const orc_stats *s, const char *file, const char *format, int tabular, int all);
 int orc_rmdup(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out, uint64_t *n_removed);
+/* -d / -D side outputs of RmDupCheck (lib/rmdup.go:180-239): removed records; "count\tid1, id2, ..." rows */
+int orc_rmdup_dups(const uint8_t *data, size_t n, const orc_opts *o, orc_out *dup_seqs, orc_out *dup_num);
 /* keys only (RmDupPrepare, lib/rmdup.go:43-90): int64 keys per record */
 int orc_rmdup_keys(const uint8_t *data, size_t n, const orc_opts *o, int64_t **keys, size_t *n_keys);
 int orc_translate(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);

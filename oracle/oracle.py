@@ -67,6 +67,7 @@ def lib():
         for f in ("orc_seq", "orc_translate", "orc_locate", "orc_grep", "orc_subseq"):
             getattr(L, f).argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out)]
         L.orc_rmdup.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out), C.POINTER(C.c_uint64)]
+        L.orc_rmdup_dups.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out), C.POINTER(_Out)]
         L.orc_rmdup_keys.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(C.POINTER(C.c_int64)),
                                      C.POINTER(C.c_size_t)]
         L.orc_stats_run.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Stats)]
@@ -216,6 +217,19 @@ def rmdup(data, opts=None):
     rc = lib().orc_rmdup(data, len(data), C.byref(o), C.byref(out), C.byref(removed))
     d, offs = _take(out, rc)
     return d, offs, removed.value
+
+
+def rmdup_dups(data, opts=None):
+    """(-d text, -D text): removed records and the "count\tid1, id2" rows (lib/rmdup.go:180-239)."""
+    keep = []
+    o = _mk_opts(opts, keep)
+    o1, o2 = _Out(), _Out()
+    rc = lib().orc_rmdup_dups(data, len(data), C.byref(o), C.byref(o1), C.byref(o2))
+    err = o1.err.decode(errors="replace")
+    d2 = C.string_at(o2.data, o2.n) if o2.n else b""
+    lib().orc_out_free(C.byref(o2))
+    d1, _ = _take(o1, rc)
+    return d1, d2
 
 
 def rmdup_keys(data, opts=None):

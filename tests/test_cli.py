@@ -46,6 +46,14 @@ def test_cli_end_to_end(lib, monkeypatch, tmp_path, capsys):
     assert (tmp_path / "o2").read_bytes() == oracle.translate(FA_SIMPLE, {"Frame": ["6"], "AllowUnknownCodon": True})[0]
     assert _run_cli(lib, monkeypatch, ["rmdup", "-s", str(fq), str(fq), "-o", str(tmp_path / "o3")]) == 0
     assert (tmp_path / "o3").read_bytes().count(b"@") >= 2
+    # rmdup -d / -D: removed records and "count\tids" rows land in the named files (flag meaning)
+    twice = tmp_path / "twice.fq"
+    twice.write_bytes(FQ_SIMPLE * 2)
+    assert _run_cli(lib, monkeypatch, ["rmdup", "-s", "-d", str(tmp_path / "d.fq"), "-D", str(tmp_path / "d.txt"), str(twice),
+                                       "-o", str(tmp_path / "o5")]) == 0
+    assert (tmp_path / "o5").read_bytes() == oracle.rmdup(FQ_SIMPLE * 2, {"BySeq": True})[0]
+    assert ((tmp_path / "d.fq").read_bytes(), (tmp_path / "d.txt").read_bytes()) == oracle.rmdup_dups(FQ_SIMPLE * 2, {"BySeq": True})
+    assert (tmp_path / "d.txt").read_bytes().startswith(b"2\t")
     capsys.readouterr()
     assert _run_cli(lib, monkeypatch, ["stats", "-T", str(fa), str(fq)]) == 0
     out = capsys.readouterr().out.split("\n")

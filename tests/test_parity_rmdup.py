@@ -142,3 +142,53 @@ def test_rmdup_tile_front_end_matches_general_path(lib, monkeypatch, opts):
             r = o.call(data)
             assert o.timings()["fused_blocks"] == 0
         assert r.data == exp[0]
+
+
+DUP_FILE_OPTS = [{"BySeq": True}, {"ByName": True}, {}, {"BySeq": True, "IgnoreCase": True},
+                 {"BySeq": True, "Config": {"LineWidth": 7}}, {"Config": {"IDNCBI": True}}]
+
+
+def _dup_files(lib, data, opts):
+    o = dict(opts, DupSeqsFile="dups.fx", DupNumFile="dups.txt")
+    with Operator("RmDup", o, lib=lib) as op:
+        r = op.call(data)
+        return r.data, op.rmdup_dup_seqs(), op.rmdup_dup_num(), op.rmdup_removed()
+
+
+def test_rmdup_dup_files_kat(lib):
+    # hand-derived from bigseqkit-lib/rmdup.go:180-239: a/c/d share ACGT, b/e share TTTT
+    d = (b"@a x\nACGT\n+\nIIII\n@b\nTTTT\n+\nIIII\n@c y\nACGT\n+\nJJJJ\n@d\nACGT\n+\nKKKK\n@e\nTTTT\n+\nIIII\n"
+         b"@f\nGG\n+\nII\n")
+    kept, seqs, num, removed = _dup_files(lib, d, {"BySeq": True})
+    assert kept == b"@a x\nACGT\n+\nIIII\n@b\nTTTT\n+\nIIII\n@f\nGG\n+\nII\n"
+    assert seqs == b"@c y\nACGT\n+\nJJJJ\n@d\nACGT\n+\nKKKK\n@e\nTTTT\n+\nIIII\n"
+    assert num == b"3\ta, c, d\n2\tb, e\n"
+    assert removed == 3
+    assert oracle.rmdup_dups(d, {"BySeq": True}) == (seqs, num)
+    # nothing removed: both empty
+    assert _dup_files(lib, d, {})[1:3] == (b"", b"")
+
+
+@pytest.mark.parametrize("opts", DUP_FILE_OPTS, ids=lambda o: str(o)[:60])
+def test_rmdup_dup_files_match_oracle(lib, opts, monkeypatch):
+    from bigseqkit_b200 import synth
+    inputs = [dup_input(21, False), dup_input(22, True), synth.fastq_reads(60 << 10, seed=87, dup_frac=0.3).tobytes()]
+    for data in inputs:
+        exp_kept = oracle.rmdup(data, opts)
+        exp = oracle.rmdup_dups(data, opts)
+        kept, seqs, num, removed = _dup_files(lib, data, opts)
+        assert kept == exp_kept[0] and removed == exp_kept[2]
+        assert (seqs, num) == exp
+        # removed + kept records together are the input's records
+        assert len(oracle.frame(seqs)) - 1 + len(exp_kept[1]) - 1 == len(oracle.frame(data)) - 1
+    # several blocks per partition: the first member of a group sits in an earlier block
+    monkeypatch.setenv("BSK_BLOCK_BYTES", "4096")
+    for data in inputs[:2]:
+        exp = oracle.rmdup_dups(data * 3, opts)
+        assert _dup_files(lib, data * 3, opts)[1:3] == exp
+
+
+def test_rmdup_dup_num_rejected_on_the_sharded_path(lib):
+    with Operator("RmDup", {"BySeq": True, "DupNumFile": "x"}, lib=lib) as op:
+        with pytest.raises(BskError):
+            op.rmdup_prepare_device(0, 0, 0, 0)
