@@ -330,6 +330,10 @@ def subseq(data, o=None, **kwargs):       # bigseqkit/subseq.go
     return _run("SubseqTransform", data, o, kwargs)
 
 
+def fq2fa(data, o=None, **kwargs):        # bigseqkit/fq2fa.go:25-39
+    return _run("Fq2Fa", data, o, kwargs)
+
+
 def translate(data, o=None, **kwargs):    # bigseqkit/translate.go
     return _run("Translate", data, o, kwargs)
 

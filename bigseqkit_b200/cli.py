@@ -106,6 +106,9 @@ def build_parser():
     p.add_argument("--gtf-tag", default="gene_id")
     _persistent(p)
 
+    p = sub.add_parser("fq2fa", help="convert FASTQ to FASTA")  # bigseqkit-cli/fq2fa.go:27-28
+    _persistent(p)
+
     p = sub.add_parser("translate", help="translate DNA/RNA to protein sequence (supporting ambiguous bases)")
     p.add_argument("-T", "--transl-table", type=int, default=1)
     p.add_argument("-f", "--frame", action="append", default=[])
@@ -171,6 +174,8 @@ def options(a):
         return "SubseqTransform", {"Config": cfg, "Chr": a.chr, "Region": a.region, "Gtf": a.gtf, "Feature": a.feature,
                                    "UpStream": a.up_stream, "DownStream": a.down_stream, "OnlyFlank": a.only_flank,
                                    "Bed": a.bed, "GtfTag": a.gtf_tag}
+    if c == "fq2fa":
+        return "Fq2Fa", {"Config": cfg}
     if c == "translate":
         return "Translate", {"Config": cfg, "TranslTable": a.transl_table, "Frame": _split_csv(a.frame) or ["1"],
                              "Trim": a.trim, "Clean": a.clean, "AllowUnknownCodon": a.allow_unknown_codon,

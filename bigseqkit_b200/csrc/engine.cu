@@ -477,6 +477,7 @@ int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
     case OP_LOCATE: rc = op_locate(bo, pid); break;
     case OP_GREP: rc = op_grep(bo); break;
     case OP_SUBSEQ: rc = op_subseq(bo); break;
+    case OP_FQ2FA: rc = op_fq2fa(bo); break;
     default: err = "unknown operator"; rc = BSK_ERR_ARG;
   }
   first_block_ = false;

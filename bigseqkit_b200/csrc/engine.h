@@ -166,6 +166,7 @@ class Engine {
   int op_locate(BlockOut &bo, int64_t pid);
   int op_grep(BlockOut &bo);
   int op_subseq(BlockOut &bo);
+  int op_fq2fa(BlockOut &bo);
   int emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, BlockOut &bo);
   void finalize_stats(bsk_stats *s);
 };

@@ -182,6 +182,19 @@ int Engine::op_subseq(BlockOut &bo) {
   return emit_records(cfg, nullptr, nullptr, bo);
 }
 
+// ------------------------------------------------------------------ Fq2Fa
+// Fq2Fa.Call (bigseqkit-lib/fq2fa.go:36-61): qualities dropped, Record.Format(0) minus the final '\n' -> ">Name\nseq"
+// on one line whatever the input's wrapping; FASTA input goes through the same formatter.
+int Engine::op_fq2fa(BlockOut &bo) {
+  int rc = check_errors();
+  if (rc != BSK_OK) return rc;
+  EmitCfg cfg{};
+  cfg.marker = '>';
+  cfg.print_name = 1;
+  cfg.print_seq = 1;
+  return emit_records(cfg, nullptr, nullptr, bo);
+}
+
 // ------------------------------------------------------------------ Stats
 // bigseqkit-lib/stats.go:48-117 (per partition) ; totals are kept with sum semantics
 int Engine::op_stats(BlockOut &bo) {

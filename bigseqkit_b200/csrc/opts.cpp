@@ -89,6 +89,7 @@ Op op_from_name(const char *n) {
   if (!strcmp(n, "Locate") || !strcmp(n, "locate")) return OP_LOCATE;
   if (!strcmp(n, "Grep") || !strcmp(n, "grep")) return OP_GREP;
   if (!strcmp(n, "SubseqTransform") || !strcmp(n, "subseq")) return OP_SUBSEQ;
+  if (!strcmp(n, "Fq2Fa") || !strcmp(n, "fq2fa")) return OP_FQ2FA;
   return OP_INVALID;
 }
 
@@ -371,6 +372,8 @@ bool parse_and_validate(Op op, const char *json, Opts &o, std::string &err, int 
       if (o.Region.empty()) { err = "one of the options needed: -r/--region, --bed, --gtf"; return false; }
       o.has_region = true;
       if (!parse_region(o.Region, "subseq", o.region_start, o.region_end, err)) return false;
+      break;
+    case OP_FQ2FA:  // bigseqkit/fq2fa.go:11-18: KitConfig only
       break;
     default:
       err = "unknown operator";

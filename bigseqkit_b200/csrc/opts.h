@@ -15,7 +15,7 @@
 
 namespace bsk {
 
-enum Op { OP_SEQ, OP_STATS, OP_RMDUP, OP_RMDUP_PREPARE, OP_TRANSLATE, OP_LOCATE, OP_GREP, OP_SUBSEQ, OP_INVALID };
+enum Op { OP_SEQ, OP_STATS, OP_RMDUP, OP_RMDUP_PREPARE, OP_TRANSLATE, OP_LOCATE, OP_GREP, OP_SUBSEQ, OP_FQ2FA, OP_INVALID };
 
 // alphabets of shenwei356/bio v0.7.0 seq/alphabet.go as used by the reference
 enum Alphabet { AB_NIL = 0, AB_DNA, AB_DNARED, AB_RNA, AB_RNARED, AB_PROTEIN, AB_UNLIMIT, AB_COUNT };

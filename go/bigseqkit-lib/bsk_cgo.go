@@ -130,6 +130,20 @@ func (t *SubseqTransform) Call(it iterator.IReadIterator[string], context api.IC
 	return t.op.call(0, it, context)
 }
 
+// ---- Fq2Fa: bigseqkit-lib/fq2fa.go:15-61 (first of the SURVEY section 8f "next" operators)
+func NewFq2Fa() any { return &Fq2Fa{} }
+
+type Fq2Fa struct {
+	base.IMapPartitions[string, string]
+	function.IAfterNone
+	op bskOp
+}
+
+func (t *Fq2Fa) Before(context api.IContext) error { return t.op.before(context, "Fq2Fa") }
+func (t *Fq2Fa) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	return t.op.call(0, it, context)
+}
+
 // ---- Translate: bigseqkit-lib/translate.go:21-145
 func NewTranslate() any { return &Translate{} }
 

@@ -1,6 +1,7 @@
 /*
  * bsk.h -- C ABI of libbsk.so, the B200-native engine behind BigSeqKit's per-record
- * operators (seq / stats / subseq / grep / locate / rmdup / translate).
+ * operators (seq / stats / subseq / grep / locate / rmdup / translate, and fq2fa as the
+ * first of the operators either side of that path).
  *
  * Every entry point replaces one piece of the reference's executor-plugin surface
  * (citations are relative to the reference tree, citiususc/BigSeqKit @3ab4862):
@@ -10,7 +11,7 @@
  *   exported factory  New<Name>() any                           | bsk_create("<Name>", opts)
  *     bigseqkit-lib/seq.go:17-19, stats.go:16,119,              |
  *     rmdup.go:23,92, translate.go:21, locate.go:19,            |
- *     grep.go:24, subseq.go:22                                  |
+ *     grep.go:24, subseq.go:22, fq2fa.go:15                     |
  *   Before(ctx): opts := StringToOptions(ctx.Vars()["opts"])    | bsk_create parses the same JSON
  *     bigseqkit-lib/seq.go:28-79, bigseqkit/helper.go:47-66     | and returns the same error text
  *   Call(it IReadIterator[string], ctx) ([]string, error)       | bsk_run_buffer / bsk_run_device

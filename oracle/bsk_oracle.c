@@ -1176,6 +1176,27 @@ int orc_subseq(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out) {
   return rc < 0 ? -1 : 0;
 }
 
+/* ------------------------------------------------------------------- fq2fa
+ * Fq2Fa.Call (lib/fq2fa.go:36-61): record.Seq.Qual = []byte{}; Format(0) minus the final '\n'. */
+int orc_fq2fa(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out) {
+  memset(out, 0, sizeof *out);
+  int ab = ab_from_type(o->SeqType, out->err);
+  if (ab < 0) return -1;
+  parser_t p; parser_init(&p, data, n, ab, o);
+  sink_t sink; memset(&sink, 0, sizeof sink);
+  buf_t ob; memset(&ob, 0, sizeof ob);
+  int rc;
+  while ((rc = parser_read(&p)) > 0) {
+    rec_t *r = &p.r;
+    format_record(&ob, r->head, r->head_len, r->seq, r->seq_len, r->qual, 0, 0, 0); /* :53-54 */
+    sink_elem(&sink, ob.p, ob.n - 1);                                               /* :56 */
+  }
+  if (rc < 0) snprintf(out->err, 512, "%s", p.err);
+  sink_to_out(&sink, out);
+  free(ob.p); parser_free(&p);
+  return rc < 0 ? -1 : 0;
+}
+
 /* ------------------------------------------------- multi-threaded CPU baseline
  * Record-aligned byte-range shards, one thread each (the restatement of
  * "IgnisHPC partitions x executor threads").  rmdup: parallel Prepare, keys

@@ -99,6 +99,8 @@ int orc_translate(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out
 int orc_locate(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
 int orc_grep(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
 int orc_subseq(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
+/* Fq2Fa.Call (lib/fq2fa.go:36-61) */
+int orc_fq2fa(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
 
 /* leaf helpers exposed for known-answer tests */
 size_t orc_subseq_range(size_t len, int start, int end, size_t *s0); /* returns length, *s0 = 0-based start */

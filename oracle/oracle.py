@@ -64,7 +64,7 @@ def lib():
         L.orc_opts_default.argtypes = [C.POINTER(_Opts)]
         L.orc_xxh64.restype = C.c_uint64
         L.orc_xxh64.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64]
-        for f in ("orc_seq", "orc_translate", "orc_locate", "orc_grep", "orc_subseq"):
+        for f in ("orc_seq", "orc_translate", "orc_locate", "orc_grep", "orc_subseq", "orc_fq2fa"):
             getattr(L, f).argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out)]
         L.orc_rmdup.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out), C.POINTER(C.c_uint64)]
         L.orc_rmdup_dups.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Opts), C.POINTER(_Out), C.POINTER(_Out)]
@@ -207,6 +207,10 @@ def grep(data, opts=None):
 
 def subseq(data, opts=None):
     return _run("orc_subseq", data, opts)
+
+
+def fq2fa(data, opts=None):
+    return _run("orc_fq2fa", data, opts)
 
 
 def rmdup(data, opts=None):

@@ -54,6 +54,8 @@ def test_cli_end_to_end(lib, monkeypatch, tmp_path, capsys):
     assert (tmp_path / "o5").read_bytes() == oracle.rmdup(FQ_SIMPLE * 2, {"BySeq": True})[0]
     assert ((tmp_path / "d.fq").read_bytes(), (tmp_path / "d.txt").read_bytes()) == oracle.rmdup_dups(FQ_SIMPLE * 2, {"BySeq": True})
     assert (tmp_path / "d.txt").read_bytes().startswith(b"2\t")
+    assert _run_cli(lib, monkeypatch, ["fq2fa", str(fq), "-o", str(tmp_path / "o6")]) == 0
+    assert (tmp_path / "o6").read_bytes() == oracle.fq2fa(FQ_SIMPLE, {})[0]
     capsys.readouterr()
     assert _run_cli(lib, monkeypatch, ["stats", "-T", str(fa), str(fq)]) == 0
     out = capsys.readouterr().out.split("\n")

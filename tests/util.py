@@ -4,7 +4,7 @@ from bigseqkit_b200.api import BskError, Operator
 
 ORACLE_FN = {
     "SeqTransform": oracle.seq, "SubseqTransform": oracle.subseq, "Translate": oracle.translate,
-    "Locate": oracle.locate, "Grep": oracle.grep,
+    "Locate": oracle.locate, "Grep": oracle.grep, "Fq2Fa": oracle.fq2fa,
 }
 
 

@@ -40,6 +40,7 @@ def main():
                              lambda: synth.fastq_reads(nbytes, seed=2), None, None),
         "seq_fasta_reads": ("SeqTransform", {}, lambda: synth.fasta_reads(nbytes // 114, read_len=100, seed=1), None, None),
         "subseq": ("SubseqTransform", {"Region": "10:-10"}, lambda: synth.fastq_reads(nbytes, seed=2), None, None),
+        "fq2fa": ("Fq2Fa", {}, lambda: synth.fastq_reads(nbytes, seed=2), None, None),
         "grep_id": ("Grep", {"Pattern": ["SIM:1:FC:3:2208:1391:14437"], "InvertMatch": True},
                     lambda: synth.fastq_reads(nbytes, seed=2), None, None),
         "locate": ("Locate", {"Pattern": panel}, lambda: synth.fasta_contigs(min(nbytes, 256 << 20), seed=4), None, 1.0),
@@ -91,7 +92,7 @@ def main():
                 threads = 1
                 sb = sample.tobytes()
                 dt, _, _ = oracle.time_c_call({"Translate": "orc_translate", "Locate": "orc_locate", "SeqTransform": "orc_seq",
-                                               "SubseqTransform": "orc_subseq", "Grep": "orc_grep"}[opn], sb, opts)
+                                               "SubseqTransform": "orc_subseq", "Grep": "orc_grep", "Fq2Fa": "orc_fq2fa"}[opn], sb, opts)
                 nr = len(oracle.frame(sb)) - 1
             line["cpu_port"] = {"records_per_s": nr / dt, "gb_per_s": sample.nbytes / dt / 1e9, "cores": threads,
                                 "sample_bytes": int(sample.nbytes)}
