@@ -65,11 +65,21 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
                                                    const u8 *__restrict__ code_fwd, const u8 *__restrict__ code_rev,
                                                    const u8 *__restrict__ lut, u8 *__restrict__ prot, DevStatus *st,
                                                    u64 seq_limit, const u32 *__restrict__ plen) {
-  __shared__ u8 s_fwd[256], s_rev[256], s_lut[4096];
+  __shared__ u8 s_fwd[256], s_rev[256];
+  __align__(16) __shared__ u8 s_lut[4096];
   __shared__ u32 s_e[2];
-  s_fwd[threadIdx.x] = code_fwd[threadIdx.x];
-  s_rev[threadIdx.x] = code_rev[threadIdx.x];
-  for (u32 i = threadIdx.x; i < 4096; i += 256) s_lut[i] = lut[i];
+  // shared code tables: IUPAC mask 1..15 in the low nibble; gap -> 0x10, not a nucleotide -> 0x20 (low nibble 0), so
+  // that one OR over a chunk's codes tells whether any codon needs the careful path
+  {
+    const u8 a = code_fwd[threadIdx.x], b = code_rev[threadIdx.x];
+    s_fwd[threadIdx.x] = a == 16 ? 0x10 : (a == 0 ? 0x20 : a);
+    s_rev[threadIdx.x] = b == 16 ? 0x10 : (b == 0 ? 0x20 : b);
+  }
+  if (((size_t)lut & 15) == 0) {  // 4096 codon entries: one 16-byte copy per thread
+    reinterpret_cast<uint4 *>(s_lut)[threadIdx.x] = reinterpret_cast<const uint4 *>(lut)[threadIdx.x];
+  } else {
+    for (u32 i = threadIdx.x; i < 4096; i += 256) s_lut[i] = lut[i];
+  }
   const u32 n_el = v.n_rec * c.nf;
   const u64 cta0 = (u64)blockIdx.x * 256ull * kTrAA;
   if (threadIdx.x < 64) {
@@ -106,49 +116,67 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
   u64 lo_addr = 0;
   if (fast) {
     lo_addr = f > 0 ? sbase + i0 : sbase + l - 48u - i0;  // lowest source byte of the 48
-    fast = (lo_addr & ~3ull) + 52 <= seq_limit;          // whole words stay inside the readable buffer
+    fast = (lo_addr & ~15ull) + 64 <= seq_limit;         // the four 16-byte loads stay inside the readable buffer
   }
   if (fast) {
     u32 nt[12];
     {
-      const u32 *wp = reinterpret_cast<const u32 *>(v.seqb + (lo_addr & ~3ull));
-      const u32 sh = (u32)(lo_addr & 3ull) * 8u;
-      u32 x[13];
+      // 48 bytes at any alignment sit inside four aligned 16-byte loads (offset <= 15, 15 + 48 <= 64); the word and
+      // byte offsets are resolved with selects and funnel shifts
+      const uint4 *vp = reinterpret_cast<const uint4 *>(v.seqb + (lo_addr & ~15ull));
+      const uint4 q0 = vp[0], q1 = vp[1], q2 = vp[2], q3 = vp[3];
+      const u32 x[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+      const u32 off = (u32)(lo_addr & 15ull);
+      const bool w1 = (off & 4u) != 0, w2 = (off & 8u) != 0;
+      const u32 sh = (off & 3u) * 8u;
+      u32 z[15], y[13];
 #pragma unroll
-      for (int q = 0; q < 13; q++) x[q] = wp[q];
+      for (int q = 0; q < 15; q++) z[q] = w1 ? x[q + 1] : x[q];
 #pragma unroll
-      for (int q = 0; q < 12; q++) nt[q] = __funnelshift_r(x[q], x[q + 1], sh);
+      for (int q = 0; q < 13; q++) y[q] = w2 ? z[q + 2] : z[q];
+#pragma unroll
+      for (int q = 0; q < 12; q++) nt[q] = __funnelshift_r(y[q], y[q + 1], sh);
     }
+    // branch-free inner loop: three code look-ups, one codon look-up, one OR into the output word per amino acid;
+    // `special` collects the gap / not-a-nucleotide flags of the codons that exist
+    u32 special = 0;
+    if (f > 0) {
 #pragma unroll
-    for (int t = 0; t < (int)kTrAA; t++) {
-      u32 c0, c1, c2;
-      if (f > 0) {
-        c0 = s_fwd[(nt[(3 * t) >> 2] >> (8 * ((3 * t) & 3))) & 0xffu];
-        c1 = s_fwd[(nt[(3 * t + 1) >> 2] >> (8 * ((3 * t + 1) & 3))) & 0xffu];
-        c2 = s_fwd[(nt[(3 * t + 2) >> 2] >> (8 * ((3 * t + 2) & 3))) & 0xffu];
-      } else {  // codon t reads the window from its top: bytes 47-3t, 46-3t, 45-3t
-        c0 = s_rev[(nt[(47 - 3 * t) >> 2] >> (8 * ((47 - 3 * t) & 3))) & 0xffu];
-        c1 = s_rev[(nt[(46 - 3 * t) >> 2] >> (8 * ((46 - 3 * t) & 3))) & 0xffu];
-        c2 = s_rev[(nt[(45 - 3 * t) >> 2] >> (8 * ((45 - 3 * t) & 3))) & 0xffu];
+      for (int t = 0; t < (int)kTrAA; t++) {
+        const u32 c0 = s_fwd[(nt[(3 * t) >> 2] >> (8 * ((3 * t) & 3))) & 0xffu];
+        const u32 c1 = s_fwd[(nt[(3 * t + 1) >> 2] >> (8 * ((3 * t + 1) & 3))) & 0xffu];
+        const u32 c2 = s_fwd[(nt[(3 * t + 2) >> 2] >> (8 * ((3 * t + 2) & 3))) & 0xffu];
+        if ((u32)t < valid) special |= c0 | c1 | c2;
+        const u32 x = s_lut[((c0 * 16u + c1) * 16u + c2) & 0xfffu];
+        w[t >> 2] |= x << (8 * (t & 3));
       }
-      u8 aa;
-      bool init = false;
-      if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
-      else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
-        aa = 'X';
-        if (!c.allow_unknown && (u32)t < valid)
-          atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
-      } else {
-        const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
-        aa = x & 0x7f;
-        init = (x & 0x80) != 0;
+    } else {  // codon t reads the window from its top: bytes 47-3t, 46-3t, 45-3t
+#pragma unroll
+      for (int t = 0; t < (int)kTrAA; t++) {
+        const u32 c0 = s_rev[(nt[(47 - 3 * t) >> 2] >> (8 * ((47 - 3 * t) & 3))) & 0xffu];
+        const u32 c1 = s_rev[(nt[(46 - 3 * t) >> 2] >> (8 * ((46 - 3 * t) & 3))) & 0xffu];
+        const u32 c2 = s_rev[(nt[(45 - 3 * t) >> 2] >> (8 * ((45 - 3 * t) & 3))) & 0xffu];
+        if ((u32)t < valid) special |= c0 | c1 | c2;
+        const u32 x = s_lut[((c0 * 16u + c1) * 16u + c2) & 0xfffu];
+        w[t >> 2] |= x << (8 * (t & 3));
       }
-      if (c.init_m && j + (u32)t == 0 && init) aa = 'M';
-      if (c.clean && aa == '*') aa = 'X';
-      w[t >> 2] |= (u32)aa << (8 * (t & 3));
     }
-    *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
-    return;
+    if ((special & 0x30u) == 0) {
+      if (c.init_m && j == 0 && (w[0] & 0x80u)) w[0] = (w[0] & ~0xffu) | (u32)'M';  // bit 7 of a table entry: start codon
+#pragma unroll
+      for (int q = 0; q < 4; q++) w[q] &= 0x7f7f7f7fu;
+      if (c.clean) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {  // '*' (0x2a) -> 'X' (0x58): bytes are < 0x80, so the zero-byte test is exact
+          const u32 y = w[q] ^ 0x2a2a2a2au;
+          const u32 z = (((y + 0x7f7f7f7fu) | y) & 0x80808080u) ^ 0x80808080u;  // 0x80 where the byte was '*'
+          w[q] ^= (z >> 7) * (u32)('*' ^ 'X');
+        }
+      }
+      *reinterpret_cast<uint4 *>(prot + a0) = make_uint4(w[0], w[1], w[2], w[3]);
+      return;
+    }
+    // a gap or a byte outside the alphabet among the chunk's codons: the careful loop below decides '-' / 'X' / error
   }
   // slow path (window would leave the buffer: first / last records of a block): byte loads, valid codons only
 #pragma unroll 1
@@ -166,8 +194,8 @@ __global__ void __launch_bounds__(256) k_translate(RecViews v, TrCfg c, const u6
     }
     u8 aa;
     bool init = false;
-    if (c0 == 16 && c1 == 16 && c2 == 16) aa = '-';
-    else if (c0 == 0 || c1 == 0 || c2 == 0 || c0 == 16 || c1 == 16 || c2 == 16) {
+    if (c0 == 0x10 && c1 == 0x10 && c2 == 0x10) aa = '-';
+    else if ((c0 | c1 | c2) & 0x30u) {
       aa = 'X';
       if (!c.allow_unknown) atomicMin((unsigned long long *)&st->err, ((unsigned long long)r << 4) | EK_UNKNOWN_CODON);
     } else {
