@@ -29,7 +29,6 @@ import (
 
 	"ignis/executor/api"
 	"ignis/executor/api/base"
-	"ignis/executor/api/function"
 	"ignis/executor/api/iterator"
 )
 
@@ -107,11 +106,11 @@ func NewSeqTransform() any { return &SeqTransform{} }
 
 type SeqTransform struct {
 	base.IMapPartitions[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *SeqTransform) Before(context api.IContext) error { return t.op.before(context, "SeqTransform") }
+func (t *SeqTransform) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *SeqTransform) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(0, it, context)
 }
@@ -121,11 +120,11 @@ func NewSubseqTransform() any { return &SubseqTransform{} }
 
 type SubseqTransform struct {
 	base.IMapPartitions[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *SubseqTransform) Before(context api.IContext) error { return t.op.before(context, "SubseqTransform") }
+func (t *SubseqTransform) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *SubseqTransform) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(0, it, context)
 }
@@ -135,11 +134,11 @@ func NewFq2Fa() any { return &Fq2Fa{} }
 
 type Fq2Fa struct {
 	base.IMapPartitions[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *Fq2Fa) Before(context api.IContext) error { return t.op.before(context, "Fq2Fa") }
+func (t *Fq2Fa) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *Fq2Fa) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(0, it, context)
 }
@@ -149,11 +148,11 @@ func NewTranslate() any { return &Translate{} }
 
 type Translate struct {
 	base.IMapPartitions[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *Translate) Before(context api.IContext) error { return t.op.before(context, "Translate") }
+func (t *Translate) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *Translate) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(0, it, context)
 }
@@ -163,11 +162,11 @@ func NewLocate() any { return &Locate{} }
 
 type Locate struct {
 	base.IMapPartitionsWithIndex[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *Locate) Before(context api.IContext) error { return t.op.before(context, "Locate") }
+func (t *Locate) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *Locate) Call(pid int64, it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(pid, it, context) // header row only in partition 0 (locate.go:198-204)
 }
@@ -176,11 +175,11 @@ func NewGrep() any { return &Grep{} }
 
 type Grep struct {
 	base.IMapPartitionsWithIndex[string, string]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *Grep) Before(context api.IContext) error { return t.op.before(context, "Grep") }
+func (t *Grep) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *Grep) Call(pid int64, it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
 	return t.op.call(pid, it, context)
 }
@@ -191,11 +190,11 @@ func NewStats() any { return &Stats{} }
 
 type Stats struct {
 	base.IMapPartitions[string, map[int64]int64]
-	function.IAfterNone
 	op bskOp
 }
 
 func (t *Stats) Before(context api.IContext) error { return t.op.before(context, "Stats") }
+func (t *Stats) After(context api.IContext) error { return t.op.after() } // frees the executor's ctxs
 func (t *Stats) Call(it iterator.IReadIterator[string], context api.IContext) ([]map[int64]int64, error) {
 	ctx := t.op.ctxs[context.ThreadId()]
 	C.bsk_reset(ctx)

@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--mib", type=int, default=512)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--ops", default="stats_fasta,stats_fastq,rmdup,translate,locate")
+    ap.add_argument("--ops", default="stats_fasta,stats_fastq,rmdup,translate,locate,subseq,grep_id,fq2fa")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle port on all host cores (seq/stats/rmdup)")
     args = ap.parse_args()
     import numpy as np
