@@ -72,7 +72,7 @@ def main():
         alg = n * alg_factor if alg_factor else n + n_out + (16 * n_rec if name == "rmdup" else 0)
         if name == "locate":
             alg = n  # rows are negligible
-        line = {"op": name, "operator": opn, "opts": {k: (v if k != "Pattern" else "1000 x 12-mer") for k, v in opts.items()},
+        line = {"op": name, "operator": opn, "opts": {k: ("1000 x 12-mer" if k == "Pattern" and len(v) > 8 else v) for k, v in opts.items()},
                 "in_bytes": n, "out_bytes": n_out, "records": n_rec, "ms_per_step": ms, "records_per_s": n_rec / ms * 1e3,
                 "gb_per_s": n / ms / 1e6, "algorithmic_bytes": alg, "whole_step_frac_of_hbm_peak": alg / ms / 1e6 / peak,
                 "gpu_launches_per_step": launches // args.steps, "fused_blocks": op.timings()["fused_blocks"]}
