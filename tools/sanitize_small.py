@@ -10,6 +10,9 @@ checks = [("SeqTransform", {"Reverse": True, "Complement": True}, fq[:-1], oracl
           ("SeqTransform", {"MinLen": 100, "Reverse": True}, fq, oracle.seq),
           ("RmDup", {"BySeq": True}, fq, lambda d, o: oracle.rmdup(d, o)[:2]),
           ("Translate", {"Frame": ["6"]}, fa, oracle.translate),
+          ("Translate", {"Frame": ["2", "-3"], "Clean": True, "InitCodonAsM": True, "AllowUnknownCodon": True},
+           fa.replace(b"ACG", b"A-N", 50), oracle.translate),
+          ("Fq2Fa", {}, fq, oracle.fq2fa),
           ("SubseqTransform", {"Region": "5:-5"}, fq, oracle.subseq)]
 for name, opts, data, fn in checks:
     with Operator(name, opts, device=0) as op:
@@ -20,3 +23,7 @@ for opts, data in (({"Tabular": True, "All": True}, fq), ({"Tabular": True}, fa)
     with Operator("Stats", opts, device=0) as op:
         op.call(data)
         print("Stats", opts, "ok" if op.stats_render() == oracle.stats(data, opts)[1] else "MISMATCH", flush=True)
+with Operator("RmDup", {"BySeq": True, "DupSeqsFile": "d", "DupNumFile": "D"}, device=0) as op:
+    op.call(fq)
+    got = (op.rmdup_dup_seqs(), op.rmdup_dup_num())
+    print("RmDup -d -D", "ok" if got == oracle.rmdup_dups(fq, {"BySeq": True}) else "MISMATCH", flush=True)
