@@ -8,9 +8,13 @@
 
 namespace bsk {
 
+struct __align__(16) TableSlot {
+  u64 key, first;
+};
+
 struct Engine::RmdupState {
-  // key -> earliest global record ordinal; open addressing, cap slots + 1 extra slot for key 0
-  u64 *tkeys = nullptr, *tfirst = nullptr;
+  // key -> earliest global record ordinal; open addressing, cap slots + 1 extra slot for the all-ones key
+  TableSlot *table = nullptr;
   u64 cap = 0, alloc_cap = 0;
   bool dirty = false;  // holds keys of a partition that has been reset
   // {xxh64 seed 0, xxh64 seed B} of every record of the partition seen so far (global input order)

@@ -47,27 +47,41 @@ __global__ void k_rmdup_hash(SubjectViews sv, u32 n_rec, int ignore_case, u64 *_
   fps[r] = b;
 }
 
-// open addressing, linear probing; key 0 lives in the extra slot `cap`
-__device__ __forceinline__ u64 table_slot(u64 *tkeys, u64 cap, u64 key, bool insert) {
-  if (key == 0) return cap;
+// open addressing, linear probing over 16-byte slots {key, earliest ordinal}: a probe touches one sector.  An empty
+// slot is all ones (one memset clears the table and sets every ordinal to "none"); that key lives in the extra slot `cap`.
+static const u64 kEmptyKey = ~0ull;
+
+__device__ __forceinline__ u64 table_insert_slot(TableSlot *t, u64 cap, u64 key) {
+  if (key == kEmptyKey) return cap;
   u64 i = (key * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
   for (;;) {
-    u64 cur = tkeys[i];
+    const u64 cur = t[i].key;
     if (cur == key) return i;
-    if (cur == 0) {
-      if (!insert) return ~0ull;
-      const u64 old = atomicCAS((unsigned long long *)&tkeys[i], 0ull, (unsigned long long)key);
-      if (old == 0 || old == key) return i;
+    if (cur == kEmptyKey) {
+      const u64 old = atomicCAS((unsigned long long *)&t[i].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (old == kEmptyKey || old == key) return i;
     }
     i = (i + 1) & (cap - 1);
   }
 }
 
-__global__ void k_table_insert(const u64 *__restrict__ keys, u64 n, u64 g_base, u64 *tkeys, u64 *tfirst, u64 cap) {
+// earliest ordinal stored for `key` (the key is known to be in the table)
+__device__ __forceinline__ u64 table_first(const TableSlot *t, u64 cap, u64 key) {
+  if (key == kEmptyKey) return t[cap].first;
+  u64 i = (key * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
+  for (;;) {
+    const ulonglong2 e = *reinterpret_cast<const ulonglong2 *>(&t[i]);
+    if (e.x == key) return e.y;
+    if (e.x == kEmptyKey) return kNoFirst;
+    i = (i + 1) & (cap - 1);
+  }
+}
+
+__global__ void k_table_insert(const u64 *__restrict__ keys, u64 n, u64 g_base, TableSlot *t, u64 cap) {
   const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const u64 s = table_slot(tkeys, cap, keys[r], true);
-  atomicMin((unsigned long long *)&tfirst[s], (unsigned long long)(g_base + r));
+  const u64 s = table_insert_slot(t, cap, keys[r]);
+  atomicMin((unsigned long long *)&t[s].first, (unsigned long long)(g_base + r));
 }
 
 __device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32 b, int ignore_case) {
@@ -87,14 +101,13 @@ __device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32
 
 // keep[r]: 1 first occurrence, 0 duplicate, 2 unresolved (64-bit key collision between different subjects)
 __global__ void k_rmdup_resolve(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *__restrict__ keys,
-                                const u64 *__restrict__ fps, u64 g_base, const u64 *__restrict__ hist_fp, u64 *tkeys,
-                                const u64 *__restrict__ tfirst, u64 cap, u8 *__restrict__ keep, u64 *__restrict__ first_out,
-                                DevStatus *st) {
+                                const u64 *__restrict__ fps, u64 g_base, const u64 *__restrict__ hist_fp,
+                                const TableSlot *__restrict__ table, u64 cap, u8 *__restrict__ keep,
+                                u64 *__restrict__ first_out, DevStatus *st) {
   const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rec) return;
   const u64 g = g_base + r;
-  const u64 s = table_slot(tkeys, cap, keys[r], false);
-  const u64 first = tfirst[s];
+  const u64 first = table_first(table, cap, keys[r]);
   u8 k;
   if (first == g) k = 1;
   else if (first >= g_base) k = subject_equal(sv, r, (u32)(first - g_base), ignore_case) ? 0 : 2;
@@ -164,28 +177,24 @@ static void table_reserve(Engine::RmdupState *rm, u64 total, cudaStream_t s, u64
   u64 cap = 1u << 12;
   while (cap < total * 4) cap *= 2;
   if (cap > rm->alloc_cap) {  // device memory is kept across bsk_reset / partitions: only growth reallocates
-    if (rm->tkeys) cudaFree(rm->tkeys);
-    if (rm->tfirst) cudaFree(rm->tfirst);
-    rm->tkeys = rm->tfirst = nullptr;
-    BSK_CUDA(cudaMalloc((void **)&rm->tkeys, (cap + 1) * 8));
-    BSK_CUDA(cudaMalloc((void **)&rm->tfirst, (cap + 1) * 8));
+    if (rm->table) cudaFree(rm->table);
+    rm->table = nullptr;
+    BSK_CUDA(cudaMalloc((void **)&rm->table, (cap + 1) * sizeof(TableSlot)));
     rm->alloc_cap = cap;
   }
-  BSK_CUDA(cudaMemsetAsync(rm->tkeys, 0, (cap + 1) * 8, s));
-  BSK_CUDA(cudaMemsetAsync(rm->tfirst, 0xff, (cap + 1) * 8, s));
+  BSK_CUDA(cudaMemsetAsync(rm->table, 0xff, (cap + 1) * sizeof(TableSlot), s));
   rm->cap = cap;
   rm->dirty = false;
   if (rm->n_hist) {
-    BSK_LAUNCH_FLAT(k_table_insert, (u32)((rm->n_hist + 255) / 256), 256, 0, s, rm->hist_keys, rm->n_hist, (u64)0, rm->tkeys,
-                    rm->tfirst, cap);
+    BSK_LAUNCH_FLAT(k_table_insert, (u32)((rm->n_hist + 255) / 256), 256, 0, s, rm->hist_keys, rm->n_hist, (u64)0, rm->table,
+                    cap);
     launches++;
   }
 }
 
 void rmdup_state_free(Engine::RmdupState *rm) {
   if (!rm) return;
-  if (rm->tkeys) cudaFree(rm->tkeys);
-  if (rm->tfirst) cudaFree(rm->tfirst);
+  if (rm->table) cudaFree(rm->table);
   if (rm->hist_keys) cudaFree(rm->hist_keys);
   if (rm->hist_fp) cudaFree(rm->hist_fp);
   delete rm;
@@ -241,10 +250,9 @@ int Engine::rmdup_resolve_block(BlockOut &bo) {
   u64 *first = want_dup_num ? b_op5_.get<u64>((size_t)n_rec_ + 1) : nullptr;
   if (n_rec_) {
     table_reserve(rm, g_base + n_rec_, stream, launches_);
-    BSK_LAUNCH_FLAT(k_table_insert, (n_rec_ + 255) / 256, 256, 0, stream, keys, (u64)n_rec_, g_base, rm->tkeys, rm->tfirst,
-                    rm->cap);
+    BSK_LAUNCH_FLAT(k_table_insert, (n_rec_ + 255) / 256, 256, 0, stream, keys, (u64)n_rec_, g_base, rm->table, rm->cap);
     BSK_LAUNCH_FLAT(k_rmdup_resolve, (n_rec_ + 255) / 256, 256, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps,
-                    g_base, rm->hist_fp, rm->tkeys, rm->tfirst, rm->cap, keep, first, d_status_);
+                    g_base, rm->hist_fp, rm->table, rm->cap, keep, first, d_status_);
     launches_ += 2;
     fetch_status();
     if (h_status_->counters[4]) {
