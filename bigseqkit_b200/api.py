@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbsk.so")
 
 BSK_OK = 0
-BSK_ERR_ARG, BSK_ERR_DATA, BSK_ERR_CUDA, BSK_ERR_UNSUPPORTED, BSK_ERR_STATE = -1, -2, -3, -4, -5
+BSK_ERR_ARG, BSK_ERR_DATA, BSK_ERR_CUDA, BSK_ERR_UNSUPPORTED, BSK_ERR_STATE, BSK_ERR_NOMEM = -1, -2, -3, -4, -5, -6
+BSK_COMM_ID_BYTES = 128
 
 
 class BskError(RuntimeError):
@@ -46,6 +47,8 @@ ABI_SYMBOLS = [
     "bsk_set_elem_offsets", "bsk_reset", "bsk_run_buffer", "bsk_run_device", "bsk_stream", "bsk_get_timings",
     "bsk_stats_result", "bsk_stats_merge", "bsk_stats_add", "bsk_stats_dense_device", "bsk_stats_render",
     "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_dup_seqs", "bsk_rmdup_dup_num", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
+    "bsk_comm_unique_id", "bsk_comm_error", "bsk_comm_init", "bsk_comm_rank", "bsk_comm_free", "bsk_output_offsets",
+    "bsk_stats_allreduce", "bsk_rmdup_sharded", "bsk_reduce", "bsk_rmdup_union", "bsk_memcpy_d2h",
 ]
 
 
@@ -89,6 +92,17 @@ class Library:
         L.bsk_rmdup_resolve_device.argtypes = [vp, vp, u64, C.POINTER(_Out)]
         L.bsk_grep_count.argtypes = [vp]
         L.bsk_grep_count.restype = u64
+        L.bsk_comm_unique_id.argtypes = [C.c_char_p]
+        L.bsk_comm_error.restype = C.c_char_p
+        L.bsk_comm_init.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+        L.bsk_comm_rank.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.bsk_comm_free.argtypes = [vp]
+        L.bsk_output_offsets.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.bsk_stats_allreduce.argtypes = [vp]
+        L.bsk_rmdup_sharded.argtypes = [vp, vp, sz, C.POINTER(_Out)]
+        L.bsk_reduce.argtypes = [C.POINTER(vp), C.c_int]
+        L.bsk_rmdup_union.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(_Out)]
+        L.bsk_memcpy_d2h.argtypes = [vp, vp, vp, sz]
 
     def device_count(self):
         return self.cdll.bsk_device_count()
@@ -290,6 +304,79 @@ class Operator:
 
     def grep_count(self):
         return self.lib.cdll.bsk_grep_count(self.h)
+
+    # ---- exchange steps (NCCL communicator bound to the ctx)
+    def comm_init(self, uid, n_ranks, rank):
+        """uid: the 128 bytes rank 0 got from `comm_unique_id()` and the driver shipped to every rank."""
+        assert len(uid) == BSK_COMM_ID_BYTES
+        self._check(self.lib.cdll.bsk_comm_init(self.h, bytes(uid), n_ranks, rank))
+
+    def comm_free(self):
+        self._check(self.lib.cdll.bsk_comm_free(self.h))
+
+    def comm_rank(self):
+        r, n = C.c_int(0), C.c_int(1)
+        self.lib.cdll.bsk_comm_rank(self.h, C.byref(r), C.byref(n))
+        return r.value, n.value
+
+    def output_offsets(self, n_local):
+        off, tot = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.cdll.bsk_output_offsets(self.h, n_local, C.byref(off), C.byref(tot)))
+        return off.value, tot.value
+
+    def stats_allreduce(self):
+        """StatsReduce over all ranks (bigseqkit/stats.go:91): afterwards this ctx holds the global totals."""
+        self._check(self.lib.cdll.bsk_stats_allreduce(self.h))
+
+    def rmdup_sharded(self, dev_ptr, nbytes):
+        """rmdup over the shards of all ranks (bigseqkit/rmdup.go:97); returns the raw struct with DEVICE pointers."""
+        out = _Out()
+        self._check(self.lib.cdll.bsk_rmdup_sharded(self.h, C.c_void_p(dev_ptr), nbytes, C.byref(out)))
+        return out
+
+    def fetch(self, out):
+        """copy a device-side result (call_device / rmdup_sharded / ...) to the host: Result with bytes + offsets"""
+        import numpy as np
+        data = np.empty(out.n, np.uint8)
+        self._check(self.lib.cdll.bsk_memcpy_d2h(self.h, data.ctypes.data, out.data, out.n))
+        offs = None
+        if out.elem_off:
+            offs = np.empty(out.n_elem + 1, np.uint64)
+            self._check(self.lib.cdll.bsk_memcpy_d2h(self.h, offs.ctypes.data, out.elem_off, offs.nbytes))
+        return data, offs
+
+
+def comm_unique_id(lib=None):
+    """rank 0: a fresh NCCL unique id (128 bytes) to ship to every rank before Operator.comm_init"""
+    lib = lib or default_library()
+    buf = C.create_string_buffer(BSK_COMM_ID_BYTES)
+    rc = lib.cdll.bsk_comm_unique_id(buf)
+    if rc != BSK_OK:
+        raise BskError(rc, lib.cdll.bsk_comm_error().decode(errors="replace"))
+    return buf.raw
+
+
+def reduce_local(ops):
+    """StatsReduce folded over several Stats operators of this process: every one ends with the sum (bsk_reduce)"""
+    lib = ops[0].lib
+    arr = (C.c_void_p * len(ops))(*[o.h for o in ops])
+    rc = lib.cdll.bsk_reduce(arr, len(ops))
+    if rc != BSK_OK:
+        raise BskError(rc, lib.cdll.bsk_last_error(ops[0].h).decode(errors="replace"))
+
+
+def rmdup_union_local(ops, dev_ptrs, sizes):
+    """rmdup over several shards held by ctxs of this process, ctx order == input order (bsk_rmdup_union)"""
+    lib = ops[0].lib
+    n = len(ops)
+    arr = (C.c_void_p * n)(*[o.h for o in ops])
+    ptrs = (C.c_void_p * n)(*dev_ptrs)
+    szs = (C.c_size_t * n)(*sizes)
+    outs = (_Out * n)()
+    rc = lib.cdll.bsk_rmdup_union(arr, n, ptrs, szs, outs)
+    if rc != BSK_OK:
+        raise BskError(rc, lib.cdll.bsk_last_error(ops[0].h).decode(errors="replace"))
+    return list(outs)
 
 
 # ---------------------------------------------------------------------------

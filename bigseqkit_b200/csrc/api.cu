@@ -25,6 +25,7 @@ struct bsk_ctx {
 
 static thread_local std::string g_create_err;
 
+// exceptions never cross the boundary; each class keeps its own status code
 #define BSK_GUARD(ctx, body)                                      \
   try {                                                           \
     body                                                          \
@@ -33,10 +34,13 @@ static thread_local std::string g_create_err;
     return BSK_ERR_CUDA;                                          \
   } catch (const std::bad_alloc &) {                              \
     (ctx)->eng->err = "out of host memory";                       \
-    return BSK_ERR_CUDA;                                          \
-  } catch (const std::exception &e) {                             \
+    return BSK_ERR_NOMEM;                                         \
+  } catch (const std::invalid_argument &e) {                      \
     (ctx)->eng->err = e.what();                                   \
-    return BSK_ERR_CUDA;                                          \
+    return BSK_ERR_ARG;                                           \
+  } catch (const std::exception &e) {                             \
+    (ctx)->eng->err = std::string("internal error: ") + e.what(); \
+    return BSK_ERR_STATE;                                         \
   }
 
 extern "C" {
@@ -350,5 +354,93 @@ int bsk_rmdup_resolve_device(bsk_ctx *ctx, const void *d_all_fp, uint64_t n_befo
 }
 
 uint64_t bsk_grep_count(const bsk_ctx *ctx) { return ctx ? ctx->eng->grep_count : 0; }
+
+int bsk_memcpy_d2h(bsk_ctx *ctx, void *h_dst, const void *d_src, size_t n) {
+  if (!ctx || (n && (!h_dst || !d_src))) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, {
+    if (n) BSK_CUDA(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, ctx->eng->stream));
+    BSK_CUDA(cudaStreamSynchronize(ctx->eng->stream));
+    return BSK_OK;
+  })
+}
+
+// ---- exchange steps
+static thread_local std::string g_comm_err;
+const char *bsk_comm_error(void) { return g_comm_err.c_str(); }
+
+int bsk_comm_unique_id(uint8_t *id) {
+  if (!id) return BSK_ERR_ARG;
+  g_comm_err.clear();
+  try {
+    return bsk::comm_unique_id(id, g_comm_err);
+  } catch (const std::exception &e) {
+    g_comm_err = e.what();
+    return BSK_ERR_CUDA;
+  }
+}
+
+int bsk_comm_init(bsk_ctx *ctx, const uint8_t *id, int n_ranks, int rank) {
+  if (!ctx || !id) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->comm_init(id, n_ranks, rank);)
+}
+
+int bsk_comm_free(bsk_ctx *ctx) {
+  if (!ctx) return BSK_ERR_ARG;
+  BSK_GUARD(ctx, { ctx->eng->comm_free(); return BSK_OK; })
+}
+
+int bsk_comm_rank(const bsk_ctx *ctx, int *rank, int *n_ranks) {
+  if (!ctx) return BSK_ERR_ARG;
+  return ctx->eng->comm_rank(rank, n_ranks);
+}
+
+int bsk_output_offsets(bsk_ctx *ctx, uint64_t n_local, uint64_t *offset, uint64_t *total) {
+  if (!ctx) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->output_offsets(n_local, offset, total);)
+}
+
+int bsk_stats_allreduce(bsk_ctx *ctx) {
+  if (!ctx) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->stats_allreduce();)
+}
+
+int bsk_rmdup_sharded(bsk_ctx *ctx, const void *d_in, size_t n, bsk_out *out) {
+  if (!ctx || !out || (!d_in && n)) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->rmdup_sharded(d_in, n, out);)
+}
+
+int bsk_reduce(bsk_ctx **ctxs, int n) {
+  if (!ctxs || n < 1) return BSK_ERR_ARG;
+  std::vector<bsk::Engine *> e;
+  for (int i = 0; i < n; i++) {
+    if (!ctxs[i]) return BSK_ERR_ARG;
+    e.push_back(ctxs[i]->eng);
+  }
+  BSK_GUARD(ctxs[0], {
+    std::string err;
+    const int rc = bsk::stats_reduce_local(e.data(), n, err);
+    if (rc != BSK_OK) ctxs[0]->eng->err = err;
+    return rc;
+  })
+}
+
+int bsk_rmdup_union(bsk_ctx **ctxs, int n, const void *const *d_in, const size_t *n_bytes, bsk_out *outs) {
+  if (!ctxs || n < 1 || !d_in || !n_bytes || !outs) return BSK_ERR_ARG;
+  std::vector<bsk::Engine *> e;
+  for (int i = 0; i < n; i++) {
+    if (!ctxs[i]) return BSK_ERR_ARG;
+    e.push_back(ctxs[i]->eng);
+  }
+  BSK_GUARD(ctxs[0], {
+    std::string err;
+    const int rc = bsk::rmdup_union_local(e.data(), n, d_in, n_bytes, outs, err);
+    if (rc != BSK_OK) ctxs[0]->eng->err = err;
+    return rc;
+  })
+}
 
 }  // extern "C"

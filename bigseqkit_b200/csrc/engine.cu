@@ -46,6 +46,7 @@ Engine::~Engine() {
   }
   if (s_in_) { cudaStreamSynchronize(s_in_); cudaStreamDestroy(s_in_); }
   if (s_out_) { cudaStreamSynchronize(s_out_); cudaStreamDestroy(s_out_); }
+  comm_free();
   free_op_state();
   if (stream) cudaStreamDestroy(stream);
 }

@@ -51,6 +51,20 @@ class Engine {
   int rmdup_dup_seqs(const char **data, size_t *n);
   int rmdup_dup_num(const char **data, size_t *n);
 
+  // exchange steps (comm.cu): NCCL communicator bound to the ctx, or several ctxs of one process
+  struct CommState;
+  int comm_init(const uint8_t *id, int n_ranks, int rank);
+  void comm_free();
+  int comm_rank(int *rank, int *n_ranks) const;
+  int output_offsets(u64 n_local, u64 *offset, u64 *total);
+  int stats_allreduce();
+  void stats_clear_totals() { hist_.clear(); q20_ = q30_ = gap_ = 0; stats_type_.clear(); stats_type_set_ = false; }
+  int rmdup_sharded(const void *d_in, size_t n, bsk_out *out);
+  int rmdup_prepare_local(const void *d_in, size_t n, u64 *n_records);  // index + hash, keys / second hashes stay on the device
+  void rmdup_export_fp(u64 *d_fp);                                      // interleaved {key, second hash} of the prepared shard
+  void rmdup_export_own_fp();
+  int rmdup_resolve_after(Engine **e, int self, const u64 *counts, bsk_out *out);
+
   struct RmdupState;   // ops_rmdup.cu: key table + fingerprint history of the running partition
   struct PatternSet;   // ops_match.cu: needles of locate / grep on the device
 
@@ -118,6 +132,9 @@ class Engine {
   std::vector<int64_t> keys_host_;
   RmdupState *rm_ = nullptr;
   PatternSet *pats_ = nullptr;
+  CommState *comm_ = nullptr;
+  DevBuf b_comm_small_, b_comm_, b_fp_, b_fp_before_;
+  void comm_gather_words(const u64 *h_mine, size_t n_words, u64 *h_all);
   u64 hit_cap_ = 0;
   int build_patterns(bool only_pos);
   int run_matcher(int mode, u8 *flags, u64 &n_hits);
@@ -170,5 +187,9 @@ class Engine {
   int emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, BlockOut &bo);
   void finalize_stats(bsk_stats *s);
 };
+
+int comm_unique_id(uint8_t *id, std::string &err);
+int stats_reduce_local(Engine **e, int n, std::string &err);
+int rmdup_union_local(Engine **e, int n, const void *const *d_in, const size_t *nbytes, bsk_out *outs, std::string &err);
 
 }  // namespace bsk

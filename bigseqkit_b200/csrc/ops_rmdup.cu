@@ -537,8 +537,8 @@ int Engine::rmdup_keys(const int64_t **keys, size_t *n) {
   return BSK_OK;
 }
 
-// multi-GPU step 1: index + hash the local shard, export {key, second hash} per record
-int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records) {
+// multi-GPU step 1: index + hash the local shard; keys / second hashes stay in b_op1_ / b_op2_
+int Engine::rmdup_prepare_local(const void *d_in, size_t n, u64 *n_records) {
   if (op_ != OP_RMDUP) { err = "bsk_rmdup_prepare_device: ctx is not an RmDup operator"; return BSK_ERR_STATE; }
   if (n >= kMaxBlockBytes) { err = "bsk_rmdup_prepare_device: shard must be smaller than 4 GiB - 1 MiB"; return BSK_ERR_ARG; }
   if (((uintptr_t)d_in & 15) != 0) { err = "bsk_rmdup_prepare_device: device pointer must be 16-byte aligned"; return BSK_ERR_ARG; }
@@ -565,14 +565,8 @@ int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t 
   rc = check_errors();
   if (rc != BSK_OK) return rc;
   if (n_records) *n_records = n_rec_;
-  if ((size_t)n_rec_ > fp_cap) { err = "bsk_rmdup_prepare_device: fingerprint buffer too small"; return BSK_ERR_ARG; }
   rc = rmdup_hash_block();
   if (rc != BSK_OK) return rc;
-  if (n_rec_) {
-    BSK_LAUNCH_FLAT(k_interleave_fp, (n_rec_ + 255) / 256, 256, 0, stream, b_op1_.as<u64>(), b_op2_.as<u64>(), (u64)n_rec_,
-                    static_cast<u64 *>(d_fp));
-    launches_++;
-  }
   BSK_CUDA(cudaEventRecord(ev_[4], stream));
   BSK_CUDA(cudaStreamSynchronize(stream));
   accumulate_timings();
@@ -580,6 +574,24 @@ int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t 
   timings.in_bytes = n;
   rm_->block_ready = true;
   first_block_ = false;
+  return BSK_OK;
+}
+
+void Engine::rmdup_export_fp(u64 *d_fp) {
+  if (!n_rec_) return;
+  BSK_LAUNCH_FLAT(k_interleave_fp, (n_rec_ + 255) / 256, 256, 0, stream, b_op1_.as<u64>(), b_op2_.as<u64>(), (u64)n_rec_, d_fp);
+  launches_++;
+}
+
+int Engine::rmdup_prepare_device(const void *d_in, size_t n, void *d_fp, size_t fp_cap, u64 *n_records) {
+  u64 nr = 0;
+  int rc = rmdup_prepare_local(d_in, n, &nr);
+  if (n_records) *n_records = nr;
+  if (rc != BSK_OK) return rc;
+  if ((size_t)nr > fp_cap) { rm_->block_ready = false; err = "bsk_rmdup_prepare_device: fingerprint buffer too small"; return BSK_ERR_ARG; }
+  rmdup_export_fp(static_cast<u64 *>(d_fp));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  timings.kernel_launches = launches_;
   return BSK_OK;
 }
 

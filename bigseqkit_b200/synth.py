@@ -150,3 +150,62 @@ def fasta_cds(nbytes, seed=5, min_len=300, max_len=3000, width=60):
         chunks += [hdr, body]
         total += hdr.size + body.size
     return np.ascontiguousarray(np.concatenate(chunks))
+
+
+# ---------------------------------------------------------------------------- native generators (libbsksynth.so)
+# Counter-based C generators of the same four shapes (synth_native.c): well under a second per GiB, independent of
+# the thread count, able to write straight into a caller buffer (e.g. pinned memory).  The benches and the
+# full-size tests use these; the numpy generators above stay for the small parity cases.
+_native = None
+
+
+def _native_lib():
+    global _native
+    if _native is None:
+        import ctypes as C
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbsksynth.so")
+        if not os.path.exists(path):
+            raise ImportError("bigseqkit_b200: %s is missing; run `make -C bigseqkit_b200/csrc`" % path)
+        L = C.CDLL(path)
+        u64, u32, vp = C.c_uint64, C.c_uint32, C.c_void_p
+        for f, at in (("bsk_synth_fastq", [vp, u64, u64, u32, u32, C.c_int, C.POINTER(u64)]),
+                      ("bsk_synth_fasta_reads", [vp, u64, u64, u32, u64, C.c_int, C.POINTER(u64)]),
+                      ("bsk_synth_contigs", [vp, u64, u64, u32, u32, u32, C.c_int, C.POINTER(u64)]),
+                      ("bsk_synth_cds", [vp, u64, u64, u32, u32, u32, C.c_int, C.POINTER(u64)])):
+            getattr(L, f).argtypes = at
+            getattr(L, f).restype = u64
+        _native = L
+    return _native
+
+
+def _native_call(fn, nbytes, out, args, threads):
+    import ctypes as C
+    import os
+    if out is None:
+        out = np.empty(int(nbytes), np.uint8)
+    assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.nbytes >= nbytes
+    nrec = C.c_uint64(0)
+    threads = threads or min(os.cpu_count() or 1, 32)
+    n = getattr(_native_lib(), fn)(out.ctypes.data, int(nbytes), *args, threads, C.byref(nrec))
+    return out[:n], int(nrec.value)
+
+
+def native_fastq(nbytes, seed=2, read_len=150, dup_frac=0.0, out=None, threads=None):
+    """C2 / C3 FASTQ reads (see synth_native.c); returns (uint8 array of whole records <= nbytes, record count)."""
+    return _native_call("bsk_synth_fastq", nbytes, out, (int(seed), int(read_len), int(round(dup_frac * 1e6))), threads)
+
+
+def native_fasta_reads(nbytes, seed=1, read_len=100, max_records=0, out=None, threads=None):
+    """C1 FASTA reads, one line per sequence."""
+    return _native_call("bsk_synth_fasta_reads", nbytes, out, (int(seed), int(read_len), int(max_records)), threads)
+
+
+def native_contigs(nbytes, seed=4, min_len=1000, max_len=5_000_000, width=60, out=None, threads=None):
+    """C4 FASTA contigs, log-uniform lengths, wrapped."""
+    return _native_call("bsk_synth_contigs", nbytes, out, (int(seed), int(min_len), int(max_len), int(width)), threads)
+
+
+def native_cds(nbytes, seed=5, min_len=300, max_len=3000, width=60, out=None, threads=None):
+    """C5 CDS-like FASTA records, lengths multiples of 3, wrapped."""
+    return _native_call("bsk_synth_cds", nbytes, out, (int(seed), int(min_len), int(max_len), int(width)), threads)

@@ -23,6 +23,10 @@
  *   Stats finalise + StatsString  bigseqkit/stats.go:75-288     | bsk_stats_result / bsk_stats_render
  *   RmDupPrepare key = int64(xxhash.Sum64(subject))             | bsk_rmdup_keys* (+ "RmDup" fused op)
  *     bigseqkit-lib/rmdup.go:67-86                              |
+ *   Stats Reduce over all partitions  bigseqkit/stats.go:91     | bsk_stats_allreduce (NCCL) / bsk_reduce
+ *   RmDup GroupByKey + RmDupCheck     bigseqkit/rmdup.go:97,    | bsk_rmdup_sharded (NCCL) / bsk_rmdup_union
+ *     bigseqkit-lib/rmdup.go:118-242                            |
+ *   FileStore token ring  bigseqkit-lib/helper.go:399-431       | bsk_output_offsets
  *   After(ctx) / plugin unload                                  | bsk_destroy
  *   error return of Before/Call                                 | negative status + bsk_last_error
  *
@@ -51,7 +55,8 @@ extern "C" {
 #define BSK_ERR_DATA (-2)        /* malformed input (reference: Call() error) */
 #define BSK_ERR_CUDA (-3)        /* CUDA runtime failure or no usable device */
 #define BSK_ERR_UNSUPPORTED (-4) /* flag combination outside the accelerated path */
-#define BSK_ERR_STATE (-5)       /* call sequence error */
+#define BSK_ERR_STATE (-5)       /* call sequence error, or an internal error that is neither CUDA nor data */
+#define BSK_ERR_NOMEM (-6)       /* out of host memory */
 
 typedef struct bsk_ctx bsk_ctx;
 
@@ -171,6 +176,44 @@ int bsk_rmdup_dup_num(bsk_ctx *ctx, const char **data, size_t *n);
  *     have an earlier equal fingerprint and emits the survivors. */
 int bsk_rmdup_prepare_device(bsk_ctx *ctx, const void *d_in, size_t n, void *d_fp, size_t fp_cap, uint64_t *n_records);
 int bsk_rmdup_resolve_device(bsk_ctx *ctx, const void *d_all_fp, uint64_t n_before, bsk_out *out);
+
+/* ---- exchange steps between partitions ------------------------------------- */
+/* The path has exactly two: StatsReduce (bigseqkit/stats.go:91, bigseqkit-lib/stats.go:128-137; sum semantics) and
+ * rmdup's GroupByKey + RmDupCheck (bigseqkit/rmdup.go:97, bigseqkit-lib/rmdup.go:118-242; the first occurrence in
+ * global input order survives).  Plus the ordered merged output file, for which the reference passes an MPI token
+ * around its executors (bigseqkit-lib/helper.go:399-431).
+ *
+ * One process per GPU (the reference: one executor per MPI rank): rank 0 calls bsk_comm_unique_id, the driver ships
+ * the 128 bytes to every rank (MPI / IgnisHPC variable / torch.distributed / a file), every rank calls
+ * bsk_comm_init on its ctx (rank order == input order).  The collectives below run on the ctx stream over NCCL
+ * (NVLink / NVSwitch); NCCL is loaded on first use (libnccl.so.2, or $BSK_NCCL_LIB). */
+#define BSK_COMM_ID_BYTES 128
+int bsk_comm_unique_id(uint8_t *id /* BSK_COMM_ID_BYTES */);
+const char *bsk_comm_error(void); /* message of the last failed bsk_comm_unique_id on this thread */
+int bsk_comm_init(bsk_ctx *ctx, const uint8_t *id, int n_ranks, int rank);
+int bsk_comm_rank(const bsk_ctx *ctx, int *rank, int *n_ranks);
+int bsk_comm_free(bsk_ctx *ctx);
+/* byte offset of this rank's output in the merged file and the total size: one all-gather of the local sizes */
+int bsk_output_offsets(bsk_ctx *ctx, uint64_t n_local, uint64_t *offset, uint64_t *total);
+/* Stats: after the call every rank's totals (bsk_stats_result / bsk_stats_render) are the global ones.  One
+ * all-reduce of a dense 65536-bin length histogram + the Q20/Q30/gap sums, one small all-gather for the record
+ * counts / type column / lengths beyond the dense range. */
+int bsk_stats_allreduce(bsk_ctx *ctx);
+/* RmDup over the shards of all ranks: hash the local shard (d_in: device pointer, whole records), all-gather the
+ * 16-byte fingerprints, drop every local record with an equal fingerprint earlier in global order, emit the
+ * survivors (out: device pointers).  Inside a shard equal keys are confirmed by comparing the subject bytes, as
+ * RmDupCheck does; across shards the 128-bit fingerprint {XXH64 seed 0, XXH64 seed 0x9E3779B97F4A7C15 ^ length}
+ * decides (the bytes live on another GPU).  Every rank must call it; a rank whose shard fails makes all ranks
+ * return an error. */
+int bsk_rmdup_sharded(bsk_ctx *ctx, const void *d_in, size_t n, bsk_out *out);
+/* Several partitions inside ONE process (the reference runs Call() once per partition on executor threads): no
+ * NCCL, plain device copies; ctx order == input order; the ctxs may sit on different devices.
+ *   bsk_reduce       StatsReduce folded over n Stats ctxs: every ctx ends with the sum of all;
+ *   bsk_rmdup_union  rmdup over n shards (d_in[i], n_bytes[i] on ctxs[i]'s device), outs[i] = survivors of shard i. */
+int bsk_reduce(bsk_ctx **ctxs, int n);
+int bsk_rmdup_union(bsk_ctx **ctxs, int n, const void *const *d_in, const size_t *n_bytes, bsk_out *outs);
+/* copy n bytes of a device result (bsk_run_device / bsk_rmdup_* outputs) to host memory, ordered after the ctx stream */
+int bsk_memcpy_d2h(bsk_ctx *ctx, void *h_dst, const void *d_src, size_t n);
 
 /* ---- grep --------------------------------------------------------------- */
 /* matched-record count of the last "Grep" call (also delivered as the element when Count is set) */

@@ -1205,18 +1205,28 @@ typedef struct {
   const char *op; const uint8_t *d; size_t n; const orc_opts *o;
   uint64_t nrec, out_bytes; int rc;
   orc_stats st;
+  int keep_out; orc_out out; /* keep_out: the shard's output is handed to the caller (orc_run_mt_out) */
 } mt_job;
+typedef int (*map_fn)(const uint8_t *, size_t, const orc_opts *, orc_out *);
+static map_fn mt_map_fn(const char *op) {
+  if (!strcmp(op, "seq")) return orc_seq;
+  if (!strcmp(op, "translate")) return orc_translate;
+  if (!strcmp(op, "locate")) return orc_locate;
+  if (!strcmp(op, "grep")) return orc_grep;
+  if (!strcmp(op, "subseq")) return orc_subseq;
+  if (!strcmp(op, "fq2fa")) return orc_fq2fa;
+  return NULL;
+}
 static void *mt_worker(void *arg) {
   mt_job *j = (mt_job *)arg;
-  if (!strcmp(j->op, "seq")) {
-    orc_out out; j->rc = orc_seq(j->d, j->n, j->o, &out);
-    j->nrec = out.n_elem; j->out_bytes = out.n; orc_out_free(&out);
-  } else if (!strcmp(j->op, "stats")) {
+  map_fn f = mt_map_fn(j->op);
+  if (!strcmp(j->op, "stats")) {
     j->rc = orc_stats_run(j->d, j->n, j->o, &j->st);
     j->nrec = j->st.num; j->out_bytes = 0;
-  } else if (!strcmp(j->op, "translate")) {
-    orc_out out; j->rc = orc_translate(j->d, j->n, j->o, &out);
-    j->nrec = out.n_elem; j->out_bytes = out.n; orc_out_free(&out);
+  } else if (f) {
+    j->rc = f(j->d, j->n, j->o, &j->out);
+    j->nrec = j->out.n_elem; j->out_bytes = j->out.n;
+    if (!j->keep_out) orc_out_free(&j->out);
   } else j->rc = -1;
   return NULL;
 }
@@ -1229,6 +1239,7 @@ typedef struct {
   size_t n_total; int tid, nthreads;
   uint64_t nrec, out_bytes; int rc;
   buf_t own;               /* lower-cased subject copies when IgnoreCase */
+  int keep_out; buf_t all; uint64_t *eoff; /* keep_out: kept records (each + '\n') and their start offsets */
 } dd_job;
 static void *dd_prepare(void *arg) {
   dd_job *j = (dd_job *)arg;
@@ -1280,19 +1291,24 @@ static void *dd_format(void *arg) {
   parser_t p; parser_init(&p, j->d, j->n, ab, j->o);
   buf_t ob, all; memset(&ob, 0, sizeof ob); memset(&all, 0, sizeof all);
   size_t c = j->rec0; int rc;
+  if (j->keep_out) j->eoff = (uint64_t *)malloc((p.n_rec + 1) * sizeof(uint64_t));
   while ((rc = parser_read(&p)) > 0) {
     if (j->keep[c++]) {
       rec_t *r = &p.r; int fq = p.is_fastq;
       format_record(&ob, r->head, r->head_len, r->seq, r->seq_len, r->qual, r->qual_len, fq, fq ? 0 : j->o->LineWidth);
+      if (j->keep_out) j->eoff[j->nrec] = all.n;
       buf_add(&all, ob.p, ob.n);
       j->nrec++;
     }
   }
   j->out_bytes = all.n;
-  free(ob.p); free(all.p); parser_free(&p);
+  free(ob.p); parser_free(&p);
+  if (j->keep_out) j->all = all; else free(all.p);
   return NULL;
 }
-int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads, uint64_t *n_records, uint64_t *out_bytes) {
+static int run_mt_impl(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads, uint64_t *n_records, uint64_t *out_bytes,
+                       orc_out *out, orc_stats *st_out) {
+  if (out) memset(out, 0, sizeof *out);
   if (threads < 1) threads = 1;
   if (threads > 256) threads = 256;
   /* record-aligned cuts: move each cut forward to the next record start */
@@ -1327,6 +1343,7 @@ int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o,
     for (int t = 0; t < threads; t++) {
       jobs[t].d = data + cut[t]; jobs[t].n = cut[t + 1] - cut[t]; jobs[t].o = o; jobs[t].keys = keys; jobs[t].subj = subj;
       jobs[t].subj_len = sl; jobs[t].keep = keep; jobs[t].n_total = total; jobs[t].tid = t; jobs[t].nthreads = threads;
+      jobs[t].keep_out = out != NULL;
     }
     for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, dd_prepare, &jobs[t]);
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
@@ -1335,10 +1352,22 @@ int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o,
     for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, dd_format, &jobs[t]);
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     for (int t = 0; t < threads; t++) { nr += jobs[t].nrec; ob += jobs[t].out_bytes; if (jobs[t].rc) rc = -1; free(jobs[t].own.p); }
+    if (out) { /* kept records of all shards in input order */
+      out->data = (uint8_t *)malloc(ob + 1); out->elem_off = (uint64_t *)malloc((nr + 1) * sizeof(uint64_t));
+      size_t pos = 0, e = 0;
+      for (int t = 0; t < threads; t++) {
+        for (size_t i = 0; i < jobs[t].nrec; i++) out->elem_off[e++] = pos + jobs[t].eoff[i];
+        if (jobs[t].all.n) memcpy(out->data + pos, jobs[t].all.p, jobs[t].all.n);
+        pos += jobs[t].all.n; free(jobs[t].all.p); free(jobs[t].eoff);
+      }
+      out->elem_off[e] = pos; out->n = pos; out->n_elem = e;
+    }
+    nr = total;
     free(keys); free(subj); free(sl); free(keep); free(jobs);
   } else {
     mt_job *jobs = (mt_job *)calloc((size_t)threads, sizeof(mt_job));
-    for (int t = 0; t < threads; t++) { jobs[t].op = op; jobs[t].d = data + cut[t]; jobs[t].n = cut[t + 1] - cut[t]; jobs[t].o = o; }
+    if (strcmp(op, "stats") && !mt_map_fn(op)) { free(jobs); return -1; }
+    for (int t = 0; t < threads; t++) { jobs[t].op = op; jobs[t].d = data + cut[t]; jobs[t].n = cut[t + 1] - cut[t]; jobs[t].o = o; jobs[t].keep_out = out != NULL; }
     for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     orc_stats merged; memset(&merged, 0, sizeof merged);
@@ -1346,10 +1375,47 @@ int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o,
       nr += jobs[t].nrec; ob += jobs[t].out_bytes; if (jobs[t].rc) rc = -1;
       if (!strcmp(op, "stats")) { orc_stats_merge(&merged, &jobs[t].st); orc_stats_free(&jobs[t].st); }
     }
-    if (!strcmp(op, "stats")) { orc_stats_finalise(&merged, o->All); nr = merged.num; ob = merged.sum_len; orc_stats_free(&merged); }
+    if (!strcmp(op, "stats")) {
+      orc_stats_finalise(&merged, o->All); nr = merged.num; ob = merged.sum_len;
+      if (st_out) *st_out = merged; else orc_stats_free(&merged);
+    } else if (out) {
+      /* elements of all shards in input order; locate prints its header row in partition 0 only (lib/locate.go:198-204) */
+      const int hdr = !strcmp(op, "locate") && !(o->Gtf || o->Bed);
+      size_t tot = 0, ne = 0;
+      for (int t = 0; t < threads; t++) { tot += jobs[t].out.n; ne += jobs[t].out.n_elem; }
+      out->data = (uint8_t *)malloc(tot + 1); out->elem_off = (uint64_t *)malloc((ne + 1) * sizeof(uint64_t));
+      size_t pos = 0, e = 0;
+      for (int t = 0; t < threads; t++) {
+        orc_out *so = &jobs[t].out;
+        size_t e0 = (hdr && t > 0 && so->n_elem) ? 1 : 0;
+        if (jobs[t].rc && !out->err[0]) memcpy(out->err, so->err, sizeof out->err);
+        if (so->n_elem > e0) {
+          const uint64_t b0 = so->elem_off[e0];
+          for (size_t i = e0; i < so->n_elem; i++) out->elem_off[e++] = pos + (so->elem_off[i] - b0);
+          memcpy(out->data + pos, so->data + b0, so->n - b0);
+          pos += so->n - b0;
+        }
+        orc_out_free(so);
+      }
+      out->elem_off[e] = pos; out->n = pos; out->n_elem = e; ob = pos;
+    }
     free(jobs);
   }
   if (n_records) *n_records = nr;
   if (out_bytes) *out_bytes = ob;
+  return rc;
+}
+int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads, uint64_t *n_records, uint64_t *out_bytes) {
+  return run_mt_impl(op, data, n, o, threads, n_records, out_bytes, NULL, NULL);
+}
+/* as orc_run_mt, but the output of the whole input is returned (shards concatenated in input order): the full-size
+ * parity checks of bench.py / tests compare it with the CUDA library's output byte for byte.  op "stats": *st receives
+ * the merged, finalised result (out stays empty).  n_records = input records (stats, rmdup) or elements (map operators). */
+int orc_run_mt_out(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads, orc_out *out, orc_stats *st,
+                   uint64_t *n_records) {
+  uint64_t ob = 0;
+  orc_stats tmp; memset(&tmp, 0, sizeof tmp);
+  int rc = run_mt_impl(op, data, n, o, threads, n_records, &ob, out, st ? st : &tmp);
+  if (!st) orc_stats_free(&tmp);
   return rc;
 }

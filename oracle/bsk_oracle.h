@@ -111,6 +111,11 @@ size_t orc_wrap_len(size_t l, int width);
  * {"seq","stats","rmdup"}; returns records processed, fills checksum of output sizes */
 int orc_run_mt(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads,
                uint64_t *n_records, uint64_t *out_bytes);
+/* same sharded run, output kept: op in {"seq","translate","locate","grep","subseq","fq2fa","rmdup"} fills *out with the
+ * elements of all shards in input order (locate: header row from shard 0 only, lib/locate.go:198-204; rmdup: first
+ * occurrence in input order over the WHOLE input); op "stats" fills *st with the merged, finalised totals. */
+int orc_run_mt_out(const char *op, const uint8_t *data, size_t n, const orc_opts *o, int threads, orc_out *out,
+                   orc_stats *st, uint64_t *n_records);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,8 @@ def lib():
         L.orc_wrap_len.argtypes = [C.c_size_t, C.c_int]
         L.orc_run_mt.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(_Opts), C.c_int,
                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_run_mt_out.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(_Opts), C.c_int, C.POINTER(_Out),
+                                     C.POINTER(_Stats), C.POINTER(C.c_uint64)]
         L.orc_out_free.argtypes = [C.POINTER(_Out)]
         L.orc_stats_free.argtypes = [C.POINTER(_Stats)]
         L.free = C.CDLL(None).free
@@ -340,6 +342,38 @@ def run_mt(op, data_ptr, n, opts, threads):
     if rc != 0:
         raise OracleError("run_mt(%s) failed" % op)
     return nr.value, ob.value
+
+
+def run_mt_full(op, data_ptr, n, opts, threads, file="input0", fmt="N/A"):
+    """Sharded run over the WHOLE input with the output kept (full-size parity checks).  data_ptr: integer address of
+    n bytes.  Returns a dict: seconds (the C call alone), records, and for op "stats" the rendered row (`row`), else
+    `data` (numpy uint8 view copy of every element + '\n') and `elem_off` (numpy uint64, n_elem + 1)."""
+    import time
+    import numpy as np
+    keep = []
+    o = _mk_opts(opts, keep)
+    out, st, nr = _Out(), _Stats(), C.c_uint64(0)
+    L = lib()
+    t0 = time.perf_counter()
+    rc = L.orc_run_mt_out(_b(op), C.c_void_p(data_ptr), n, C.byref(o), threads, C.byref(out), C.byref(st), C.byref(nr))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        err = out.err.decode(errors="replace")
+        L.orc_out_free(C.byref(out))
+        L.orc_stats_free(C.byref(st))
+        raise OracleError("run_mt_full(%s): %s" % (op, err))
+    res = {"seconds": dt, "records": nr.value}
+    if op == "stats":
+        p = L.orc_stats_render(C.byref(st), _b(file), _b(fmt), o.Tabular, o.All)
+        res["row"] = C.string_at(p).decode()
+        res["stats"] = _stats_dict(st)
+        L.free(p)
+        L.orc_stats_free(C.byref(st))
+    else:
+        res["data"] = np.ctypeslib.as_array(out.data, shape=(out.n,)).copy() if out.n else np.zeros(0, np.uint8)
+        res["elem_off"] = np.ctypeslib.as_array(out.elem_off, shape=(out.n_elem + 1,)).copy() if out.elem_off else np.zeros(1, np.uint64)
+        L.orc_out_free(C.byref(out))
+    return res
 
 
 def elements(data, offs):
