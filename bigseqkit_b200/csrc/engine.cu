@@ -448,6 +448,20 @@ int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
     bo = BlockOut();
     BSK_CUDA(cudaEventRecord(ev_[0], stream));
   }
+  if (op_ == OP_LOCATE) {
+    const int frc = op_locate_tile(d_in, n, pid, bo);
+    if (frc != kFusedFallback) {
+      first_block_ = false;
+      if (frc == BSK_OK) {
+        BSK_CUDA(cudaEventRecord(ev_[4], stream));
+        BSK_CUDA(cudaStreamSynchronize(stream));
+        accumulate_timings();
+      }
+      return frc;
+    }
+    bo = BlockOut();
+    BSK_CUDA(cudaEventRecord(ev_[0], stream));
+  }
   if (op_ == OP_RMDUP || op_ == OP_RMDUP_PREPARE) {
     const int frc = op_rmdup_tile(d_in, n, bo, op_ == OP_RMDUP_PREPARE);
     if (frc != kFusedFallback) {

@@ -137,6 +137,9 @@ class Engine {
   void comm_gather_words(const u64 *h_mine, size_t n_words, u64 *h_all);
   u64 hit_cap_ = 0;
   int build_patterns(bool only_pos);
+  int build_kmer_tables();
+  int op_locate_tile(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo);
+  int locate_rows(BlockOut &bo, int64_t pid, u64 n_hits);
   int run_matcher(int mode, u8 *flags, u64 &n_hits);
   int finish_grep_count(BlockOut &bo);
   int rmdup_hash_block();
@@ -174,7 +177,7 @@ class Engine {
   u32 first_rec_bytes_ = 0;
   u32 first_seq_len_ = 0;  // sequence length of the partition's first record (lane-group choice of the tile kernels)
   DevBuf b_tile_cnt_, b_tile_base_, b_slots_;
-  int first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok);
+  int first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok, bool long_ok = false);
   DevBuf b_tiles_;
   PinnedBuf h_probe_;
   int op_stats(BlockOut &bo);

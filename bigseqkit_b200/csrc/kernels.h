@@ -127,6 +127,34 @@ void rmdup_tile(const u8 *in, u32 n, void *slots, u32 *tile_cnt, DevStatus *st, 
 void rmdup_tile_compact(const void *slots, const u32 *tile_cnt, const u64 *tile_base, u32 n_tiles, u64 *keys, u64 *fps,
                         RecArrays ra, u32 *id_len, cudaStream_t s);
 
+// ---- locate with an equal-length ACGT panel on FASTA, one streaming pass over the raw bytes (k_locate_tile.cu)
+struct LocateTileArgs {
+  const u8 *in;
+  u32 n, n_tiles;
+  const u8 *lut;        // 256 byte classes (lt::C_*)
+  const u32 *filter;    // Bloom bitmap of the needle codes, locate_tile_filter_bits() bits (copied to shared memory)
+  u32 kmul, kmul2;      // bit index i = (code * kmul_i) >> (32 - bits); kmul_i = odd << (32 - 2L)
+  u32 L, cmask;         // pattern length, mask of the 2L code bits
+  const u32 *table;     // exact table: pairs {code, first needle + 1 (0 = empty)}, open addressing
+  u32 tmask, tshift;
+  const u32 *nd_code, *nd_ps;  // needles sorted by code: code, pattern << 1 | strand
+  u32 n_needles;
+  u64 *hitA, *hitB;     // raw hits: A = newlines of the tile in front << 32 | position of the last base, B = tile << 32 | ps
+  u64 hit_cap;
+  u64 *hdr_off, *hdr_nl;  // header lines: position of '>', newlines of its tile in front of it
+  u64 hdr_cap;
+  u32 *tile_nl;         // newlines per tile (owned range)
+  DevStatus *st;        // counters[0] declined tiles, [5] hits, [6] header lines
+};
+u32 locate_tile_tiles(u32 n);
+u32 locate_tile_bytes();
+u32 locate_tile_filter_bits();
+void locate_tile(LocateTileArgs a, int n_sm, cudaStream_t s);
+void locate_records(const u8 *in, u32 n, const u64 *hdr_off, const u64 *hdr_nl, const u32 *tile_nl_base, u32 n_tiles, u32 n_rec,
+                    u32 *name_off, u32 *name_len, u32 *seq_start, u32 *seq_nl, u32 *seq_len, cudaStream_t s);
+void locate_resolve(u64 *hitA, u64 *hitB, u64 n_hits, const u64 *hdr_off, u32 n_rec, const u32 *tile_nl_base, const u32 *seq_start,
+                    const u32 *seq_nl, const u32 *seq_len, u32 L, cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

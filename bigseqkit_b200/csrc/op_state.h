@@ -51,6 +51,12 @@ struct Engine::PatternSet {
   DevBuf name_hash;  // u64 per pattern (sorted)
   DevBuf name_meta;  // u32 x 2 per pattern: offset, len into pat_bytes (same order as name_hash)
   u32 n_names = 0;
+  // host copy of the needles (group order) and, for an equal-length ACGT panel, the 2-bit tables of k_locate_tile.cu
+  std::vector<std::string> needle_s;
+  std::vector<u32> needle_ps;
+  bool kmer_built = false, kmer_ok = false;
+  u32 kL = 0, kfbits = 0, kmul = 0, kmul2 = 0, kcmask = 0, ktmask = 0, ktshift = 0, kn = 0;
+  DevBuf klut, kfilter, ktable, kcode, kps;
 };
 
 void rmdup_state_free(Engine::RmdupState *rm);

@@ -60,7 +60,7 @@ bool Engine::seq_fused_eligible() const {
 
 // Alphabet of the partition from its first record (SeqParser.Read on record 0 + GuessAlphabetLessConservatively,
 // bigseqkit-lib/helper.go:219-291), done on the host from a 256 KiB probe of the block.
-int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) {
+int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok, bool long_ok) {
   ok = false;
   const u32 probe = n < (256u << 10) ? n : (256u << 10);
   h_probe_.reserve(probe + 16);
@@ -79,7 +79,9 @@ int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) 
     found = true;
     break;
   }
-  if (!found) return BSK_OK;  // first record longer than the probe: not a short-record block
+  // first record longer than the probe: not a short-record block; with long_ok the guess is still made when the
+  // probe holds as many bases as the guess looks at (contigs)
+  if (!found && !long_ok) return BSK_OK;
   if (end > 0 && d[end - 1] == '\n') end--;  // ReadFixer strips one trailing newline
   u32 p = 0;
   while (p < end && d[p] != '\n') p++;  // header line
@@ -101,6 +103,7 @@ int Engine::first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok) 
       p = q + 1;
     }
   }
+  if (!found && seq.size() < limit) return BSK_OK;
   first_seq_len_ = (u32)seq.size();
   first_rec_bytes_ = end + 1;
   if (seq.size() > limit) seq.resize(limit);

@@ -395,6 +395,9 @@ int Engine::build_patterns(bool only_pos) {
   }
   ps.n_needles = id;
   ps.n_groups = (u32)by_len.size();
+  for (auto &kv : by_len)
+    for (auto &nd : kv.second) { ps.needle_s.push_back(nd.s); ps.needle_ps.push_back((nd.pat << 1) | nd.strand); }
+  ps.kmer_built = false;
   // pattern names + text for the locate rows, hashes for grep by id/name
   std::vector<u8> pb;
   std::vector<u32> pm;
@@ -491,11 +494,6 @@ int Engine::run_matcher(int mode, u8 *flags, u64 &n_hits) {
 int Engine::op_locate(BlockOut &bo, int64_t pid) {
   int rc = check_errors();
   if (rc != BSK_OK) return rc;
-  const bool tabular = !(o_.Gtf || o_.Bed);
-  std::string header;
-  if (tabular && pid == 0 && first_block_)  // locate.go:198-204: header row only in partition 0
-    header = o_.HideMatched ? "seqID\tpatternName\tpattern\tstrand\tstart\tend\n"
-                            : "seqID\tpatternName\tpattern\tstrand\tstart\tend\tmatched\n";
   bool only_pos = o_.OnlyPositiveStrand;
   if (n_rec_ && (alphabet_ == AB_UNLIMIT || alphabet_ == AB_PROTEIN)) only_pos = true;  // locate.go:424-429 (+ Q8)
   u64 n_hits = 0;
@@ -505,6 +503,202 @@ int Engine::op_locate(BlockOut &bo, int64_t pid) {
     rc = run_matcher(0, nullptr, n_hits);
     if (rc != BSK_OK) return rc;
   }
+  return locate_rows(bo, pid, n_hits);
+}
+
+// equal-length ACGT panel: 2-bit codes of the needles, Bloom bitmap for shared memory, exact table (host, once)
+int Engine::build_kmer_tables() {
+  PatternSet &ps = *pats_;
+  if (ps.kmer_built) return BSK_OK;
+  ps.kmer_built = true;
+  ps.kmer_ok = false;
+  if (ps.needle_s.empty() || o_.Circular) return BSK_OK;
+  const size_t L = ps.needle_s[0].size();
+  if (L < 2 || L > 16) return BSK_OK;
+  bool upper = false, lower = false;
+  for (auto &sd : ps.needle_s) {
+    if (sd.size() != L) return BSK_OK;
+    for (unsigned char c : sd) {
+      if (c == 'A' || c == 'C' || c == 'G' || c == 'T') upper = true;
+      else if (c == 'a' || c == 'c' || c == 'g' || c == 't') lower = true;
+      else return BSK_OK;
+    }
+  }
+  if (upper && lower) return BSK_OK;
+  // byte classes (k_locate_tile.cu lt::C_*): valid base 8 | 16, other sequence byte 4 | 16, '\n' 0, header mark 4 | 32
+  std::vector<u8> lut(256, 4 | 16);
+  lut['\n'] = 0;
+  lut[0x01] = 4 | 32;
+  auto base = [&](char up, u8 code) {
+    if (upper || o_.IgnoreCase) lut[(u8)up] = (u8)(8 | 16 | code);
+    if (lower || o_.IgnoreCase) lut[(u8)(up + 32)] = (u8)(8 | 16 | code);
+  };
+  base('A', 0); base('C', 1); base('G', 2); base('T', 3);
+  const u32 cmask = L == 16 ? 0xffffffffu : ((1u << (2 * L)) - 1u);
+  struct Nd { u32 code, ps; };
+  std::vector<Nd> nd;
+  for (size_t i = 0; i < ps.needle_s.size(); i++) {
+    u32 code = 0;
+    for (unsigned char c : ps.needle_s[i]) code = code * 4u + (lut[c] & 3u);
+    nd.push_back(Nd{code & cmask, ps.needle_ps[i]});
+  }
+  std::stable_sort(nd.begin(), nd.end(), [](const Nd &x, const Nd &y) { return x.code < y.code; });
+  const u32 fbits = k::locate_tile_filter_bits();
+  const u32 kmul = 0x9E3779B1u << (32 - 2 * L), kmul2 = 0x85EBCA6Bu << (32 - 2 * L);
+  std::vector<u32> filter((1u << fbits) / 32, 0);
+  u32 tsize = 16;
+  while (tsize < nd.size() * 4) tsize *= 2;
+  u32 tshift = 32;
+  for (u32 t = tsize; t > 1; t >>= 1) tshift--;
+  std::vector<u32> table(2 * (size_t)tsize, 0), codes, pss;
+  for (size_t i = 0; i < nd.size(); i++) {
+    codes.push_back(nd[i].code);
+    pss.push_back(nd[i].ps);
+    const u32 bi = (nd[i].code * kmul) >> (32 - fbits), bi2 = (nd[i].code * kmul2) >> (32 - fbits);
+    filter[bi >> 5] |= 1u << (bi & 31);
+    filter[bi2 >> 5] |= 1u << (bi2 & 31);
+    if (i > 0 && nd[i - 1].code == nd[i].code) continue;  // the table points at the first needle of a code run
+    u32 slot = (nd[i].code * 0x9E3779B1u) >> tshift;
+    while (table[2 * slot + 1]) slot = (slot + 1) & (tsize - 1);
+    table[2 * slot] = nd[i].code;
+    table[2 * slot + 1] = (u32)i + 1;
+  }
+  ps.kL = (u32)L; ps.kfbits = fbits; ps.kmul = kmul; ps.kmul2 = kmul2; ps.kcmask = cmask; ps.ktmask = tsize - 1; ps.ktshift = tshift;
+  ps.kn = (u32)nd.size();
+  upload(ps.klut, lut, stream);
+  upload(ps.kfilter, filter, stream);
+  upload(ps.ktable, table, stream);
+  upload(ps.kcode, codes, stream);
+  upload(ps.kps, pss, stream);
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  ps.kmer_ok = true;
+  return BSK_OK;
+}
+
+// locate on FASTA with an equal-length ACGT panel: one streaming pass over the raw block (k_locate_tile.cu), no record
+// index.  kFusedFallback when the panel / the block is outside that kernel's grammar (the general path then runs).
+int Engine::op_locate_tile(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
+  if (n == 0 || !fused_ok_ || o_.Circular || getenv("BSK_NO_LOCATE_TILE")) return kFusedFallback;
+  bool fastq = false, ok = false;
+  const int saved_alpha = alphabet_;
+  const bool saved_known = alphabet_known_;
+  auto decline = [&]() { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; };
+  if (!alphabet_known_ || first_block_) {
+    int rc = first_record_alphabet(d_in, n, fastq, ok, true);
+    if (rc != BSK_OK) return rc;
+    if (!ok || fastq) return decline();
+  } else if (part_fastq_) {
+    return kFusedFallback;
+  }
+  bool only_pos = o_.OnlyPositiveStrand;
+  if (alphabet_ == AB_UNLIMIT || alphabet_ == AB_PROTEIN) only_pos = true;  // locate.go:424-429 (+ Q8)
+  int rc = build_patterns(only_pos);
+  if (rc != BSK_OK) return decline();
+  rc = build_kmer_tables();
+  if (rc != BSK_OK || !pats_->kmer_ok) return decline();
+  PatternSet &ps = *pats_;
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, device_ >= 0 ? device_ : 0));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  reset_status();
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  const u32 n_tiles = k::locate_tile_tiles(n);
+  k::LocateTileArgs a;
+  memset(&a, 0, sizeof a);
+  a.in = d_in;
+  a.n = n;
+  a.lut = ps.klut.as<u8>();
+  a.filter = ps.kfilter.as<u32>();
+  a.kmul = ps.kmul;
+  a.kmul2 = ps.kmul2;
+  a.L = ps.kL;
+  a.cmask = ps.kcmask;
+  a.table = ps.ktable.as<u32>();
+  a.tmask = ps.ktmask;
+  a.tshift = ps.ktshift;
+  a.nd_code = ps.kcode.as<u32>();
+  a.nd_ps = ps.kps.as<u32>();
+  a.n_needles = ps.kn;
+  a.hdr_cap = (u64)n / 32 + 1024;
+  a.hdr_off = b_op1_.get<u64>((size_t)a.hdr_cap * 2);
+  a.hdr_nl = a.hdr_off + a.hdr_cap;
+  a.tile_nl = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
+  a.st = d_status_;
+  BSK_CUDA(cudaMemsetAsync(a.tile_nl + n_tiles, 0, 4, stream));
+  u64 n_hits = 0, n_hdr = 0;
+  for (;;) {
+    if (hit_cap_ == 0) hit_cap_ = 1u << 20;
+    a.hitA = b_op3_.get<u64>(hit_cap_);
+    a.hitB = b_op4_.get<u64>(hit_cap_);
+    a.hit_cap = hit_cap_;
+    BSK_CUDA(cudaMemsetAsync(&d_status_->counters[5], 0, 16, stream));
+    main_begin();
+    k::locate_tile(a, n_sm_, stream);
+    main_end();
+    launches_++;
+    fetch_status();
+    if (h_status_->counters[0]) {
+      main_timed_ = false;
+      timings.main_launches--;
+      return decline();
+    }
+    n_hits = h_status_->counters[5];
+    n_hdr = h_status_->counters[6];
+    if (n_hdr > a.hdr_cap) {  // short records: the general path indexes them
+      main_timed_ = false;
+      timings.main_launches--;
+      return decline();
+    }
+    if (n_hits <= hit_cap_) break;
+    hit_cap_ = n_hits + n_hits / 4 + 1024;  // the hit buffer was too small: grow and match again
+    timings.main_launches--;
+  }
+  // record table: headers in input order, newline prefix over the tiles
+  n_rec_ = (u32)n_hdr;
+  const size_t R = (size_t)n_rec_ + 1;
+  u64 *hs_off = b_op5_.get<u64>(R * 2), *hs_nl = hs_off + R;
+  prim::sort_pairs_u64_u64(a.hdr_off, hs_off, a.hdr_nl, hs_nl, n_rec_, 0, 32, b_tmp_, stream);
+  u32 *tile_base = b_tile_base_.get<u32>((size_t)n_tiles + 1);
+  prim::excl_scan_u32(a.tile_nl, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  u32 *rec = b_rec_.get<u32>(R * 5);
+  u32 *name_off = rec, *name_len = rec + R, *seq_start = rec + 2 * R, *seq_nl = rec + 3 * R, *seq_len = rec + 4 * R;
+  k::locate_records(d_in, n, hs_off, hs_nl, tile_base, n_tiles, n_rec_, name_off, name_len, seq_start, seq_nl, seq_len, stream);
+  k::locate_resolve(a.hitA, a.hitB, n_hits, hs_off, n_rec_, tile_base, seq_start, seq_nl, seq_len, ps.kL, stream);
+  launches_ += 2;
+  // the block state the row formatter reads
+  in_ = d_in;
+  n_ = n;
+  fastq_ = false;
+  squeezed_ = false;
+  if (first_block_) part_fastq_ = false;
+  memset(&ra_, 0, sizeof ra_);
+  ra_.head_off = name_off;
+  ra_.head_len = name_len;
+  ra_.seq_len = seq_len;
+  views_ = RecViews{};
+  views_.in = d_in;
+  views_.seqb = d_in;
+  views_.qualb = d_in;
+  views_.name_off = name_off;
+  views_.name_len = name_len;
+  views_.seq_off = seq_start;
+  views_.seq_len = seq_len;
+  views_.n_rec = n_rec_;
+  bo.n_rec = n_rec_;
+  if (n_rec_) any_record_ = true;
+  timings.fused_blocks++;
+  return locate_rows(bo, pid, n_hits);
+}
+
+// hits (A = record << 32 | pattern << 1 | strand, B = strand coordinate << 32 | start) in b_op3_ / b_op4_ -> rows
+int Engine::locate_rows(BlockOut &bo, int64_t pid, u64 n_hits) {
+  const bool tabular = !(o_.Gtf || o_.Bed);
+  std::string header;
+  if (tabular && pid == 0 && first_block_)  // locate.go:198-204: header row only in partition 0
+    header = o_.HideMatched ? "seqID\tpatternName\tpattern\tstrand\tstart\tend\n"
+                            : "seqID\tpatternName\tpattern\tstrand\tstart\tend\tmatched\n";
   const size_t H = (size_t)n_hits + 1;
   u64 *A = b_op3_.as<u64>(), *B = b_op4_.as<u64>();
   const u8 *keep = nullptr;
