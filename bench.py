@@ -328,6 +328,7 @@ def main_ours(args):
     h_np = h_in.numpy()
     d_buf = torch.empty(cap + 64, dtype=torch.uint8, device=dev)
     h_out = torch.empty(cap, dtype=torch.uint8).pin_memory() if world > 1 else None  # survivors of the sharded rmdup
+    cp_stream = torch.cuda.Stream(device=dev)
     if args.e2e_block_mib:
         os.environ["BSK_BLOCK_BYTES"] = str(args.e2e_block_mib << 20)
 
@@ -433,9 +434,9 @@ def main_ours(args):
             def e2e_step():
                 if name == "rmdup" and collective:
                     # host -> HBM, exchange over NCCL, survivors -> host
-                    with torch.cuda.stream(ext):
+                    with torch.cuda.stream(cp_stream):  # a torch-owned stream: pinned tensors must not be tied to the ctx stream
                         d_buf[:n].copy_(h_in[:n], non_blocking=True)
-                    ext.synchronize()
+                    cp_stream.synchronize()
                     o = op.rmdup_sharded(d_buf.data_ptr(), n)
                     op._check(op.lib.cdll.bsk_memcpy_d2h(op.h, h_out.data_ptr(), o.data, o.n))
                     return int(o.n)

@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "bsk_stats_result", "bsk_stats_merge", "bsk_stats_add", "bsk_stats_dense_device", "bsk_stats_render",
     "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_dup_seqs", "bsk_rmdup_dup_num", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
     "bsk_comm_unique_id", "bsk_comm_error", "bsk_comm_init", "bsk_comm_rank", "bsk_comm_free", "bsk_output_offsets",
-    "bsk_stats_allreduce", "bsk_rmdup_sharded", "bsk_reduce", "bsk_rmdup_union", "bsk_memcpy_d2h",
+    "bsk_stats_allreduce", "bsk_rmdup_sharded", "bsk_reduce", "bsk_rmdup_union", "bsk_memcpy_d2h", "bsk_stage_device",
 ]
 
 
@@ -103,6 +103,7 @@ class Library:
         L.bsk_reduce.argtypes = [C.POINTER(vp), C.c_int]
         L.bsk_rmdup_union.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(_Out)]
         L.bsk_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+        L.bsk_stage_device.argtypes = [vp, vp, sz, C.POINTER(vp)]
 
     def device_count(self):
         return self.cdll.bsk_device_count()

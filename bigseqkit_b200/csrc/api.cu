@@ -364,6 +364,12 @@ int bsk_memcpy_d2h(bsk_ctx *ctx, void *h_dst, const void *d_src, size_t n) {
   })
 }
 
+int bsk_stage_device(bsk_ctx *ctx, const uint8_t *in, size_t n, void **d_ptr) {
+  if (!ctx || !d_ptr || (!in && n)) return BSK_ERR_ARG;
+  ctx->eng->err.clear();
+  BSK_GUARD(ctx, return ctx->eng->stage_device(in, n, d_ptr);)
+}
+
 // ---- exchange steps
 static thread_local std::string g_comm_err;
 const char *bsk_comm_error(void) { return g_comm_err.c_str(); }

@@ -44,6 +44,7 @@ struct Block {
   std::vector<std::unique_ptr<std::barrier<>>> wbar;
   std::vector<uint64_t> wslot;  // 32 slots per warp
   std::vector<uint8_t> dyn;     // dynamic shared memory
+  std::atomic<int> red{0};      // __syncthreads_or scratch
 };
 extern Block *g_block;
 extern thread_local dim3 t_threadIdx, t_blockIdx;
@@ -62,6 +63,15 @@ inline uint64_t *wslots() { return &g_block->wslot[(t_threadIdx.x >> 5) * 32]; }
 
 static inline void __syncthreads() { emu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync_warp(); }
+static inline int __syncthreads_or(int p) {
+  if (p) emu::g_block->red.fetch_or(1);
+  emu::sync_block();
+  const int r = emu::g_block->red.load();
+  emu::sync_block();
+  if (emu::t_threadIdx.x == 0) emu::g_block->red.store(0);
+  emu::sync_block();
+  return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }

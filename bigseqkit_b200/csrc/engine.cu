@@ -67,6 +67,16 @@ int Engine::reset() {
   return BSK_OK;
 }
 
+int Engine::stage_device(const u8 *in, size_t n, void **d_ptr) {
+  if (n >= kMaxBlockBytes) { err = "bsk_stage_device: partition must be smaller than 4 GiB - 1 MiB"; return BSK_ERR_ARG; }
+  if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
+  u8 *d = b_in_.get<u8>(n + 64);
+  if (n) BSK_CUDA(cudaMemcpyAsync(d, in, n, cudaMemcpyHostToDevice, stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  *d_ptr = d;
+  return BSK_OK;
+}
+
 void Engine::reset_status() {
   memset(h_status_, 0, sizeof(DevStatus));
   h_status_->err = kNoErr;
@@ -448,8 +458,8 @@ int Engine::process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
     bo = BlockOut();
     BSK_CUDA(cudaEventRecord(ev_[0], stream));
   }
-  if (op_ == OP_LOCATE) {
-    const int frc = op_locate_tile(d_in, n, pid, bo);
+  if (op_ == OP_LOCATE || op_ == OP_TRANSLATE) {
+    const int frc = op_ == OP_LOCATE ? op_locate_tile(d_in, n, pid, bo) : op_translate_tile(d_in, n, bo);
     if (frc != kFusedFallback) {
       first_block_ = false;
       if (frc == BSK_OK) {

@@ -34,6 +34,7 @@ class Engine {
   int run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out);
   int run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out);
   int reset();
+  int stage_device(const u8 *in, size_t n, void **d_ptr);  // host partition -> the ctx's own device buffer
   // pinned staging buffer of bsk_run_file (kept across calls)
   u8 *file_arena(size_t n) { h_file_.reserve(n + 64); return h_file_.as<u8>(); }
 
@@ -174,6 +175,8 @@ class Engine {
   int op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg, const u8 *h_lut, bool need_lut, BlockOut &bo);
   int op_stats_tile(const u8 *d_in, u32 n, BlockOut &bo);
   int n_sm_ = 0;
+  u32 part_width_ = 0;  // line width of the running FASTA partition (0 = unwrapped), from its first block
+  bool part_width_known_ = false;
   u32 first_rec_bytes_ = 0;
   u32 first_seq_len_ = 0;  // sequence length of the partition's first record (lane-group choice of the tile kernels)
   DevBuf b_tile_cnt_, b_tile_base_, b_slots_;
@@ -183,6 +186,8 @@ class Engine {
   int op_stats(BlockOut &bo);
   int op_rmdup(BlockOut &bo, bool prepare_only);
   int op_translate(BlockOut &bo);
+  int op_translate_tile(const u8 *d_in, u32 n, BlockOut &bo);
+  void translate_host_tables(u8 *tab);
   int op_locate(BlockOut &bo, int64_t pid);
   int op_grep(BlockOut &bo);
   int op_subseq(BlockOut &bo);

@@ -155,6 +155,47 @@ void locate_records(const u8 *in, u32 n, const u64 *hdr_off, const u64 *hdr_nl, 
 void locate_resolve(u64 *hitA, u64 *hitB, u64 n_hits, const u64 *hdr_off, u32 n_rec, const u32 *tile_nl_base, const u32 *seq_start,
                     const u32 *seq_nl, const u32 *seq_len, u32 L, cudaStream_t s);
 
+// ---- FASTA record table in one streaming pass over the raw bytes (k_fasta_tile.cu)
+struct FastaTileArgs {
+  const u8 *in;
+  u32 n, n_tiles;
+  u32 width;            // line width every record must be wrapped at (0: one sequence line per record)
+  u8 *clean;            // one byte per 96-byte span: bit j = 16-byte chunk j holds only A, C, G, T, '\n'
+  u64 *hdr_off, *hdr_nl;  // header lines: position of '>', newlines of its tile in front of it
+  u64 hdr_cap;
+  u32 *tile_nl;         // newlines per tile
+  DevStatus *st;        // counters[0] tiles that break the line shape, [6] header lines, [7] no final newline
+};
+u32 fasta_tile_tiles(u32 n);
+u32 fasta_tile_bytes();
+u32 fasta_tile_spans_per_tile();
+void fasta_index_tile(FastaTileArgs a, int n_sm, cudaStream_t s);
+
+// ---- translate on wrapped FASTA read in place, proteins formatted straight into the output (k_translate_tile.cu)
+struct TranslateTileArgs {
+  const u8 *in;
+  u32 n;
+  const u8 *clean;                      // span flags of fasta_index_tile
+  u32 n_rec, nf;
+  int frames[8];
+  const u32 *name_off, *name_len, *seq_start, *seq_len;  // record table
+  u32 width_in, width_out;              // wrap width of the input lines (0 = one line) / of the proteins (0 = one line)
+  unsigned long long magic_in, magic_out1;  // ceil(2^40 / width_in), ceil(2^40 / (width_out + 1))
+  const u64 *out_off;                   // n_rec * nf + 1 element offsets
+  u32 *tile_first;                      // scratch: translate_tile_tiles(total) entries
+  u64 total;
+  const u8 *code_fwd, *code_rev, *lut;  // IUPAC base codes (strand, complement strand), 4096-entry codon table
+  const u8 *aa_fwd, *aa_rev;            // 64-entry tables for plain ACGT codons (clean applied), index = b0 | b1 << 2 | b2 << 4
+  u64 start_fwd, start_rev;             // bit per 64-entry index: start codon (-M)
+  int allow_unknown, init_m, clean_stop;
+  u8 *out;
+  DevStatus *st;
+};
+void translate_sizes(const u32 *name_len, const u32 *seq_len, u32 n_rec, u32 nf, const int *frames, u32 width_out, u32 *sizes,
+                     DevStatus *st, cudaStream_t s);
+u32 translate_tile_tiles(u64 total);
+void translate_tile(const TranslateTileArgs &a, cudaStream_t s);
+
 // ---- stats (k_stats.cu)
 void stats_qual_gap(RecViews v, const u8 *gap, int fq_offset, int fastq, DevStatus *st, cudaStream_t s);
 

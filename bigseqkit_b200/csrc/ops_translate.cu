@@ -275,31 +275,10 @@ static u32 iupac_mask(u8 c) {  // bit0=T/U bit1=C bit2=A bit3=G (NCBI TCAG order
   return 0;
 }
 
-int Engine::op_translate(BlockOut &bo) {
-  if (n_rec_ == 0) return BSK_OK;
-  // translate.go:116-122: the partition's alphabet must be DNA/RNA; a parse error on record 0 comes first
-  const bool nucleic = alphabet_ == AB_DNA || alphabet_ == AB_DNARED || alphabet_ == AB_RNA || alphabet_ == AB_RNARED;
-  if (!nucleic && first_block_) {
-    if (h_status_->err != kNoErr && (h_status_->err >> 4) == 0) return check_errors();
-    err = "command 'seqkit translate' only apply to DNA/RNA sequences";
-    return BSK_ERR_DATA;
-  }
-  TrCfg c;
-  memset(&c, 0, sizeof c);
-  c.nf = (u32)std::min<size_t>(o_.frames.size(), 66);
-  for (u32 i = 0; i < c.nf; i++) c.frames[i] = o_.frames[i];
-  c.allow_unknown = o_.AllowUnknownCodon;
-  c.init_m = o_.InitCodonAsM;
-  c.clean = o_.Clean;
-  c.trim = o_.Trim;
-  if (c.nf == 0) return check_errors();
-  const u64 n_el64 = (u64)n_rec_ * c.nf;
-  if (n_el64 >= 0xFFFFFFF0ull) { err = "translate: too many (record, frame) elements in one block"; return BSK_ERR_DATA; }
-  const u32 n_el = (u32)n_el64;
-
-  // host tables: base -> 4-bit IUPAC code (16 = '-'), codon (3 codes) -> amino acid | 0x80 when every expansion is a start codon
+// host tables: base -> 4-bit IUPAC code (16 = '-') for both strands, codon (3 codes) -> amino acid | 0x80 when every
+// expansion is a start codon (512 + 4096 bytes)
+void Engine::translate_host_tables(u8 *tab) {
   const GCode *gc = find_gcode(o_.TranslTable);
-  u8 *tab = h_small_.as<u8>();
   const u8 *pair = alphabet_pair(alphabet_);
   for (int b = 0; b < 256; b++) {
     tab[b] = b == '-' ? 16 : (u8)iupac_mask((u8)b);
@@ -327,6 +306,222 @@ int Engine::op_translate(BlockOut &bo) {
         }
         lut[(m0 << 8) | (m1 << 4) | m2] = out;
       }
+}
+
+// translate on FASTA wrapped at one width (or unwrapped), sequences read in place: record table from one streaming
+// pass (k_fasta_tile.cu), element sizes from the record table alone, one output-driven kernel (k_translate_tile.cu).
+// kFusedFallback when the options or the block are outside that path (--trim needs the proteins before their sizes are
+// known, -F builds new headers, FASTQ input, ragged wrapping, no final newline).
+int Engine::op_translate_tile(const u8 *d_in, u32 n, BlockOut &bo) {
+  if (n == 0 || !fused_ok_ || o_.Trim || o_.AppendFrame || o_.LineWidth > 1000 || o_.frames.empty() || o_.frames.size() > 8 || getenv("BSK_NO_TRANSLATE_TILE"))
+    return kFusedFallback;
+  bool fastq = false, ok = false;
+  const int saved_alpha = alphabet_;
+  const bool saved_known = alphabet_known_;
+  auto decline = [&]() { alphabet_ = saved_alpha; alphabet_known_ = saved_known; return kFusedFallback; };
+  if (!alphabet_known_ || first_block_) {
+    part_width_known_ = false;
+    int rc = first_record_alphabet(d_in, n, fastq, ok, true);
+    if (rc != BSK_OK) return rc;
+    if (!ok || fastq) return decline();
+  } else if (part_fastq_) {
+    return kFusedFallback;
+  }
+  const bool nucleic = alphabet_ == AB_DNA || alphabet_ == AB_DNARED || alphabet_ == AB_RNA || alphabet_ == AB_RNARED;
+  if (!nucleic) return decline();  // the general path reports the error
+  // line width of the block: the first sequence line (inside the probe) that is followed by another sequence line
+  u32 width = part_width_;
+  if (first_block_ || !part_width_known_) {
+    width = 0;
+    const u8 *p = h_probe_.as<u8>();
+    const u32 pn = n < (256u << 10) ? n : (256u << 10);
+    u32 ls = 0;
+    bool prev_seq = false;
+    u32 prev_len = 0;
+    for (u32 i = 0; i <= pn && !width; i++) {
+      if (i == pn || p[i] == '\n') {
+        if (i == pn) break;
+        const bool is_hdr = p[ls] == '>';
+        if (!is_hdr && prev_seq) width = prev_len;
+        prev_seq = !is_hdr;
+        prev_len = i - ls;
+        ls = i + 1;
+      }
+    }
+    if (width > 1000) return decline();
+    part_width_ = width;
+    part_width_known_ = true;
+  }
+  if (!n_sm_) {
+    cudaDeviceProp prop;
+    BSK_CUDA(cudaGetDeviceProperties(&prop, device_ >= 0 ? device_ : 0));
+    n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  }
+  reset_status();
+  const u32 n_tiles = k::fasta_tile_tiles(n);
+  const size_t n_spans = (size_t)n_tiles * k::fasta_tile_spans_per_tile() + 4;
+  k::FastaTileArgs ia;
+  memset(&ia, 0, sizeof ia);
+  ia.in = d_in;
+  ia.n = n;
+  ia.width = width;
+  ia.clean = b_op2_.get<u8>(n_spans);
+  ia.hdr_cap = (u64)n / 32 + 1024;
+  ia.hdr_off = b_op1_.get<u64>((size_t)ia.hdr_cap * 2);
+  ia.hdr_nl = ia.hdr_off + ia.hdr_cap;
+  ia.tile_nl = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
+  ia.st = d_status_;
+  BSK_CUDA(cudaMemsetAsync(ia.clean, 0, n_spans, stream));
+  BSK_CUDA(cudaMemsetAsync(ia.tile_nl + n_tiles, 0, 4, stream));
+  k::fasta_index_tile(ia, n_sm_, stream);
+  launches_++;
+  fetch_status();
+  const u64 n_hdr = h_status_->counters[6];
+  if (h_status_->counters[0] || h_status_->counters[7] || n_hdr > ia.hdr_cap || n_hdr * o_.frames.size() >= 0xFFFFFFF0ull) return decline();
+  n_rec_ = (u32)n_hdr;
+  const size_t R = (size_t)n_rec_ + 1;
+  u64 *hs_off = b_op5_.get<u64>(R * 2), *hs_nl = hs_off + R;
+  prim::sort_pairs_u64_u64(ia.hdr_off, hs_off, ia.hdr_nl, hs_nl, n_rec_, 0, 32, b_tmp_, stream);
+  u32 *tile_base = b_tile_base_.get<u32>((size_t)n_tiles + 1);
+  prim::excl_scan_u32(ia.tile_nl, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
+  u32 *rec = b_rec_.get<u32>(R * 5);
+  u32 *name_off = rec, *name_len = rec + R, *seq_start = rec + 2 * R, *seq_nl = rec + 3 * R, *seq_len = rec + 4 * R;
+  k::locate_records(d_in, n, hs_off, hs_nl, tile_base, n_tiles, n_rec_, name_off, name_len, seq_start, seq_nl, seq_len, stream);
+  launches_++;
+  BSK_CUDA(cudaEventRecord(ev_[1], stream));
+  // the block state error reporting reads
+  in_ = d_in;
+  n_ = n;
+  fastq_ = false;
+  squeezed_ = false;
+  if (first_block_) part_fastq_ = false;
+  memset(&ra_, 0, sizeof ra_);
+  ra_.head_off = name_off;
+  ra_.head_len = name_len;
+  ra_.seq_len = seq_len;
+  views_ = RecViews{};
+  views_.in = d_in;
+  views_.seqb = d_in;
+  views_.qualb = d_in;
+  views_.name_off = name_off;
+  views_.name_len = name_len;
+  views_.seq_off = seq_start;
+  views_.seq_len = seq_len;
+  views_.qual_len = seq_len;
+  views_.n_rec = n_rec_;
+  bo.n_rec = n_rec_;
+  if (n_rec_) any_record_ = true;
+  if (n_rec_ == 0) { timings.fused_blocks++; return BSK_OK; }
+
+  const u32 nf = (u32)o_.frames.size();
+  const u32 n_el = n_rec_ * nf;
+  int frames[8];
+  for (u32 i = 0; i < 8; i++) frames[i] = i < nf ? o_.frames[i] : 1;
+  const u32 wout = o_.LineWidth > 0 ? (u32)o_.LineWidth : 0;
+  u32 *sizes = b_out_len_.get<u32>((size_t)n_el + 1);
+  u64 *out_off = b_out_off_.get<u64>((size_t)n_el + 1);
+  k::translate_sizes(name_len, seq_len, n_rec_, nf, frames, wout, sizes, d_status_, stream);
+  launches_++;
+  prim::excl_scan_u32_to_u64(sizes, out_off, (size_t)n_el + 1, b_tmp_, stream);
+  u8 *hs = h_small_.as<u8>() + 8192;
+  BSK_CUDA(cudaMemcpyAsync(hs, out_off + n_el, 8, cudaMemcpyDeviceToHost, stream));
+  // tables while the scan runs
+  u8 *tab = h_small_.as<u8>();
+  translate_host_tables(tab);
+  const GCode *gc = find_gcode(o_.TranslTable);
+  u8 *aa = tab + 512 + 4096;  // 64 + 64 entries for plain ACGT codons; base codes of the kernel: A 0, C 1, T 2, G 3
+  u64 start_fwd = 0, start_rev = 0;
+  static const int ncbi_of[4] = {2, 1, 0, 3};  // kernel code -> index in NCBI's TCAG order
+  for (int idx = 0; idx < 64; idx++) {
+    const int b0 = idx & 3, b1 = (idx >> 2) & 3, b2 = (idx >> 4) & 3;
+    const int fi = ncbi_of[b0] * 16 + ncbi_of[b1] * 4 + ncbi_of[b2];
+    const int ri = ncbi_of[b2 ^ 2] * 16 + ncbi_of[b1 ^ 2] * 4 + ncbi_of[b0 ^ 2];  // complement: code ^ 2
+    u8 x = (u8)gc->aas[fi], y = (u8)gc->aas[ri];
+    if (o_.Clean && x == '*') x = 'X';
+    if (o_.Clean && y == '*') y = 'X';
+    aa[idx] = x;
+    aa[64 + idx] = y;
+    if (gc->starts[fi] == 'M') start_fwd |= 1ull << idx;
+    if (gc->starts[ri] == 'M') start_rev |= 1ull << idx;
+  }
+  u8 *d_tab = b_op3_.get<u8>(512 + 4096 + 128);
+  BSK_CUDA(cudaMemcpyAsync(d_tab, tab, 512 + 4096 + 128, cudaMemcpyHostToDevice, stream));
+  fetch_status();  // the sizes pass flags sequences shorter than one codon
+  int rc = check_errors();
+  if (rc != BSK_OK) return rc;
+  u64 total;
+  memcpy(&total, hs, 8);
+  u8 *out = b_out_.get<u8>((size_t)total + 64);
+  k::TranslateTileArgs ta;
+  memset(&ta, 0, sizeof ta);
+  ta.in = d_in;
+  ta.n = n;
+  ta.clean = ia.clean;
+  ta.n_rec = n_rec_;
+  ta.nf = nf;
+  for (u32 i = 0; i < 8; i++) ta.frames[i] = frames[i];
+  ta.name_off = name_off;
+  ta.name_len = name_len;
+  ta.seq_start = seq_start;
+  ta.seq_len = seq_len;
+  ta.width_in = width;
+  ta.width_out = wout;
+  ta.magic_in = width ? ((1ull << 40) + width - 1) / width : 0;
+  ta.magic_out1 = ((1ull << 40) + wout) / (wout + 1ull);
+  ta.tile_first = b_op4_.get<u32>((size_t)k::translate_tile_tiles(total) + 1);
+  ta.out_off = out_off;
+  ta.total = total;
+  ta.code_fwd = d_tab;
+  ta.code_rev = d_tab + 256;
+  ta.lut = d_tab + 512;
+  ta.aa_fwd = d_tab + 512 + 4096;
+  ta.aa_rev = d_tab + 512 + 4096 + 64;
+  ta.start_fwd = start_fwd;
+  ta.start_rev = start_rev;
+  ta.allow_unknown = o_.AllowUnknownCodon;
+  ta.init_m = o_.InitCodonAsM;
+  ta.clean_stop = o_.Clean;
+  ta.out = out;
+  ta.st = d_status_;
+  main_begin();
+  k::translate_tile(ta, stream);
+  main_end();
+  launches_ += 2;
+  fetch_status();
+  rc = check_errors();
+  if (rc != BSK_OK) return rc;
+  bo.d_data = out;
+  bo.n = total;
+  bo.n_elem = n_el;
+  bo.d_elem_off = want_elem_off ? out_off : nullptr;
+  timings.fused_blocks++;
+  return BSK_OK;
+}
+
+int Engine::op_translate(BlockOut &bo) {
+  if (n_rec_ == 0) return BSK_OK;
+  // translate.go:116-122: the partition's alphabet must be DNA/RNA; a parse error on record 0 comes first
+  const bool nucleic = alphabet_ == AB_DNA || alphabet_ == AB_DNARED || alphabet_ == AB_RNA || alphabet_ == AB_RNARED;
+  if (!nucleic && first_block_) {
+    if (h_status_->err != kNoErr && (h_status_->err >> 4) == 0) return check_errors();
+    err = "command 'seqkit translate' only apply to DNA/RNA sequences";
+    return BSK_ERR_DATA;
+  }
+  TrCfg c;
+  memset(&c, 0, sizeof c);
+  c.nf = (u32)std::min<size_t>(o_.frames.size(), 66);
+  for (u32 i = 0; i < c.nf; i++) c.frames[i] = o_.frames[i];
+  c.allow_unknown = o_.AllowUnknownCodon;
+  c.init_m = o_.InitCodonAsM;
+  c.clean = o_.Clean;
+  c.trim = o_.Trim;
+  if (c.nf == 0) return check_errors();
+  const u64 n_el64 = (u64)n_rec_ * c.nf;
+  if (n_el64 >= 0xFFFFFFF0ull) { err = "translate: too many (record, frame) elements in one block"; return BSK_ERR_DATA; }
+  const u32 n_el = (u32)n_el64;
+
+  u8 *tab = h_small_.as<u8>();
+  translate_host_tables(tab);
   u8 *d_tab = b_op1_.get<u8>(512 + 4096);
   BSK_CUDA(cudaMemcpyAsync(d_tab, tab, 512 + 4096, cudaMemcpyHostToDevice, stream));
 

@@ -2,11 +2,18 @@
 // hot path on a B200 through libbsk.so (include/bsk.h).  NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Go
 // toolchain, IgnisHPC absent): it is the binding a BigSeqKit maintainer adds next to bigseqkit-lib/*.go.
 //
-// The plugin keeps the reference's exported factories (bigseqkit-lib/seq.go:17-19 NewSeqTransform, stats.go
-// NewStats / NewStatsReduce, rmdup.go NewRmDupPrepare / NewRmDupCheck, translate.go NewTranslate, locate.go
-// NewLocate, grep.go NewGrep, subseq.go NewSubseqTransform), the same embedded base.I... types and the same
-// "opts" JSON variable (bigseqkit/helper.go:47-66), so IgnisHPC and the drivers (bigseqkit/, bigseqkit-py/,
-// bigseqkit-cli/) see an identical plugin.
+// The plugin keeps the reference's exported factories with their element types (bigseqkit-lib/seq.go:17-19
+// NewSeqTransform, stats.go:16 NewStats, stats.go:119 NewStatsReduce, rmdup.go:23 NewRmDupPrepare, translate.go:21
+// NewTranslate, locate.go:19 NewLocate, grep.go:24 NewGrep, subseq.go:22 NewSubseqTransform, fq2fa.go:15 NewFq2Fa),
+// the same embedded base.I... types and the same "opts" JSON variable (bigseqkit/helper.go:47-66), so IgnisHPC and
+// the UNCHANGED drivers (bigseqkit/, bigseqkit-py/, bigseqkit-cli/) see an identical plugin:
+//   stats   bigseqkit/stats.go:86-94   MapPartitions(Stats) -> Reduce(StatsReduce): both defined here;
+//   rmdup   bigseqkit/rmdup.go:92-108  MapPartitions(RmDupPrepare) -> GroupByKey -> Flatmap(RmDupCheck):
+//           RmDupPrepare (the pass that parses, hashes and formats every record) is defined here and returns
+//           IPair[int64, string] like the reference; RmDupCheck stays the reference's own Go code
+//           (bigseqkit-lib/rmdup.go:92-275 is kept in the plugin: per-group host logic on groups of 1-2 strings).
+// NewRmDupSharded at the end is the optional faster rmdup (one exchange of 16-byte fingerprints over NCCL instead of
+// shuffling every record through GroupByKey); it needs the three-line driver patch shown in INTEGRATION.md.
 //
 // Build (inside ignishpc/go-compiler, with libbsk.so and bsk.h installed):
 //   CGO_CFLAGS="-I/opt/bsk/include" CGO_LDFLAGS="-L/opt/bsk/lib -lbsk" go build -buildmode=plugin -trimpath -o bigseqkit.so
@@ -29,6 +36,7 @@ import (
 
 	"ignis/executor/api"
 	"ignis/executor/api/base"
+	"ignis/executor/api/ipair"
 	"ignis/executor/api/iterator"
 )
 
@@ -97,6 +105,45 @@ func (o *bskOp) call(pid int64, it iterator.IReadIterator[string], context api.I
 		for i := 0; i < n; i++ {
 			res[i] = string(data[off[i] : off[i+1]-1]) // element without the '\n' FileStore adds back
 		}
+	}
+	return res, nil
+}
+
+// callSharded: the partition goes to HBM once (bsk_run_buffer on a Prepare-free path is not enough here: the exchange
+// needs the shard resident), bsk_rmdup_sharded does hash -> all-gather -> resolve, the survivors come back through
+// bsk_memcpy_d2h.  Device staging is done by libbsk (bsk_stage_device) so that no CUDA call appears in Go.
+func (o *bskOp) callSharded(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
+	ctx := o.ctxs[0]
+	buf := make([]byte, 0, 64<<20)
+	for it.HasNext() {
+		e, err := it.Next()
+		if err != nil {
+			return nil, err
+		}
+		buf = append(buf, e...)
+		buf = append(buf, '\n')
+	}
+	var dptr unsafe.Pointer
+	var p *C.uint8_t
+	if len(buf) > 0 {
+		p = (*C.uint8_t)(unsafe.Pointer(&buf[0]))
+	}
+	if rc := C.bsk_stage_device(ctx, p, C.size_t(len(buf)), &dptr); rc != C.BSK_OK {
+		return nil, fmt.Errorf("%s", C.GoString(C.bsk_last_error(ctx)))
+	}
+	var out C.bsk_out
+	if rc := C.bsk_rmdup_sharded(ctx, dptr, C.size_t(len(buf)), &out); rc != C.BSK_OK {
+		return nil, fmt.Errorf("%s", C.GoString(C.bsk_last_error(ctx)))
+	}
+	data := make([]byte, int(out.n))
+	off := make([]uint64, int(out.n_elem)+1)
+	if out.n > 0 {
+		C.bsk_memcpy_d2h(ctx, unsafe.Pointer(&data[0]), unsafe.Pointer(out.data), out.n)
+		C.bsk_memcpy_d2h(ctx, unsafe.Pointer(&off[0]), unsafe.Pointer(out.elem_off), C.size_t(8*len(off)))
+	}
+	res := make([]string, int(out.n_elem))
+	for i := range res {
+		res[i] = string(data[off[i] : off[i+1]-1])
 	}
 	return res, nil
 }
@@ -225,19 +272,96 @@ func (t *Stats) Call(it iterator.IReadIterator[string], context api.IContext) ([
 	return []map[int64]int64{m}, nil
 }
 
-// ---- RmDup: the reference's Prepare -> GroupByKey -> Check pipeline shuffles every record; the accelerated
-// operator removes duplicates inside a partition in one call ("RmDup"), and exposes the int64 keys
-// (bsk_rmdup_keys) for drivers that keep the GroupByKey exchange across partitions.
-func NewRmDupPrepare() any { return &RmDup{} }
+// ---- StatsReduce: bigseqkit-lib/stats.go:119-137, the function bigseqkit/stats.go:91 hands to Reduce.  Sum
+// semantics (SURVEY Q2: the snapshot's `result[k] = v` drops counts as soon as there are two partitions); the
+// alphabet tag -4 keeps the first partition's value.
+func NewStatsReduce() any { return &StatsReduce{} }
+
+type StatsReduce struct {
+	base.IReduce[map[int64]int64]
+	base.IOnlyCall
+}
+
+func (t *StatsReduce) Call(v1 map[int64]int64, v2 map[int64]int64, context api.IContext) (map[int64]int64, error) {
+	for k, v := range v2 {
+		if k == -4 {
+			if _, ok := v1[k]; !ok {
+				v1[k] = v
+			}
+			continue
+		}
+		v1[k] += v
+	}
+	return v1, nil
+}
+
+// ---- RmDupPrepare: bigseqkit-lib/rmdup.go:23-90.  Same element type as the reference --
+// IPair[int64(xxhash.Sum64(subject)), Record.Format(LineWidth)] -- so bigseqkit/rmdup.go:92-108 (GroupByKey, then the
+// reference's own RmDupCheck) runs unchanged.  One bsk_run_buffer call per partition parses, hashes (XXH64 on the
+// device, bit-exact with cespare/xxhash) and formats; bsk_rmdup_keys returns the keys in record order.
+func NewRmDupPrepare() any { return &RmDupPrepare{} }
+
+type RmDupPrepare struct {
+	base.IMapPartitions[string, ipair.IPair[int64, string]]
+	op bskOp
+}
+
+func (t *RmDupPrepare) Before(context api.IContext) error { return t.op.before(context, "RmDupPrepare") }
+func (t *RmDupPrepare) After(context api.IContext) error  { return t.op.after() }
+func (t *RmDupPrepare) Call(it iterator.IReadIterator[string], context api.IContext) ([]ipair.IPair[int64, string], error) {
+	vals, err := t.op.call(0, it, context)
+	if err != nil {
+		return nil, err
+	}
+	ctx := t.op.ctxs[context.ThreadId()]
+	var kp *C.int64_t
+	var kn C.size_t
+	if rc := C.bsk_rmdup_keys(ctx, &kp, &kn); rc != C.BSK_OK {
+		return nil, fmt.Errorf("%s", C.GoString(C.bsk_last_error(ctx)))
+	}
+	if int(kn) != len(vals) {
+		return nil, fmt.Errorf("bigseqkit-b200: %d keys for %d records", int(kn), len(vals))
+	}
+	keys := unsafe.Slice((*int64)(unsafe.Pointer(kp)), int(kn))
+	res := make([]ipair.IPair[int64, string], len(vals))
+	for i := range vals {
+		res[i] = *ipair.New(keys[i], vals[i]+"\n") // Format() ends in '\n' (rmdup.go:86); RmDupCheck re-parses it
+	}
+	return res, nil
+}
+
+// ---- RmDupSharded (optional, needs the driver patch of INTEGRATION.md): the whole rmdup of bigseqkit/rmdup.go:92-108
+// as ONE MapPartitions.  Every executor hashes its partition on its GPU, the executors exchange 16-byte fingerprints
+// with one NCCL all-gather (bsk_rmdup_sharded) and each keeps the records whose subject was not seen earlier in
+// global input order -- instead of moving every record through the GroupByKey shuffle.  One partition per executor
+// (the driver repartitions to Executors()); the NCCL unique id travels through the executors' MPI group.
+func NewRmDupSharded() any { return &RmDup{} }
 
 type RmDup struct {
 	base.IMapPartitions[string, string]
 	op bskOp
 }
 
-func (t *RmDup) Before(context api.IContext) error { return t.op.before(context, "RmDup") }
+func (t *RmDup) Before(context api.IContext) error {
+	if err := t.op.before(context, "RmDup"); err != nil {
+		return err
+	}
+	id := make([]byte, C.BSK_COMM_ID_BYTES)
+	if context.ExecutorId() == 0 {
+		if rc := C.bsk_comm_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0]))); rc != C.BSK_OK {
+			return fmt.Errorf("%s", C.GoString(C.bsk_comm_error()))
+		}
+	}
+	if err := context.MpiGroup().Bcast(id, 0); err != nil { // 128 bytes from executor 0 to all
+		return err
+	}
+	if rc := C.bsk_comm_init(t.op.ctxs[0], (*C.uint8_t)(unsafe.Pointer(&id[0])), C.int(context.Executors()), C.int(context.ExecutorId())); rc != C.BSK_OK {
+		return fmt.Errorf("%s", C.GoString(C.bsk_last_error(t.op.ctxs[0])))
+	}
+	return nil
+}
 func (t *RmDup) Call(it iterator.IReadIterator[string], context api.IContext) ([]string, error) {
-	return t.op.call(0, it, context)
+	return t.op.callSharded(it, context)
 }
 
 // After writes the -d / -D files per executor like bigseqkit-lib/rmdup.go:245-275 (flag meaning, not the

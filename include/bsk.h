@@ -212,6 +212,10 @@ int bsk_rmdup_sharded(bsk_ctx *ctx, const void *d_in, size_t n, bsk_out *out);
  *   bsk_rmdup_union  rmdup over n shards (d_in[i], n_bytes[i] on ctxs[i]'s device), outs[i] = survivors of shard i. */
 int bsk_reduce(bsk_ctx **ctxs, int n);
 int bsk_rmdup_union(bsk_ctx **ctxs, int n, const void *const *d_in, const size_t *n_bytes, bsk_out *outs);
+/* copy a host partition (< 4 GiB - 1 MiB) into a device buffer owned by the ctx; *d_ptr stays valid until the next
+ * bsk_stage_device / bsk_run_buffer on the ctx.  For bindings that feed bsk_run_device / bsk_rmdup_sharded without
+ * touching the CUDA runtime themselves (the Go shim). */
+int bsk_stage_device(bsk_ctx *ctx, const uint8_t *in, size_t n, void **d_ptr);
 /* copy n bytes of a device result (bsk_run_device / bsk_rmdup_* outputs) to host memory, ordered after the ctx stream */
 int bsk_memcpy_d2h(bsk_ctx *ctx, void *h_dst, const void *d_src, size_t n);
 
