@@ -363,7 +363,7 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
   const bool try_contig = !squeezed_ && n_rec_ && cfg.marker && cfg.print_name && cfg.print_seq && !cfg.reverse && !lut &&
                           views_.seqb == in_ && (fastq_ ? (cfg.print_qual && cfg.plus_line && views_.qualb == in_) : !cfg.print_qual) &&
                           getenv("BSK_NO_CONTIG") == nullptr;
-  if (try_contig) {
+  if (try_contig && !contig_known_) {
     BSK_CUDA(cudaMemsetAsync(&d_status_->counters[7], 0, 8, stream));
     k::contig_check(views_, cfg, keep, fastq_ ? 1 : 0, n_, &d_status_->counters[7], stream);
     launches_++;
@@ -375,7 +375,8 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
   u32 nsel = n_rec_;
   if (keep) memcpy(&nsel, hs + 8, 4);
   u64 not_contig = 1;
-  if (try_contig) memcpy(&not_contig, hs + 16, 8);
+  if (try_contig && !contig_known_) memcpy(&not_contig, hs + 16, 8);
+  else if (try_contig) not_contig = 0;
   u8 *out = b_out_.get<u8>((size_t)total + 64);
   main_begin();
   if (not_contig == 0) {

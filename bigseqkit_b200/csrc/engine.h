@@ -115,6 +115,7 @@ class Engine {
   u64 launches_ = 0;
   cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, indexed, main0, main1, end
   bool main_timed_ = false;
+  bool contig_known_ = false;  // the caller vouches that every kept record is printed exactly as it stands in the input
   void main_begin();
   void main_end();
   void accumulate_timings();

@@ -5,9 +5,9 @@
 //   RmDupPrepare.Call                        bigseqkit-lib/rmdup.go:43-90   key = int64(xxhash.Sum64(subject)),
 //                                            subject = seq (-s) | Name (-n) | ID (default)
 //
-// Same skeleton as k_stats_tile.cu (tile_common.cuh).  Every owned record is hashed from shared memory by one
-// thread (XXH64 seed 0 + a second seeded XXH64 for the 128-bit fingerprint, 8-byte little-endian words assembled
-// from aligned 32-bit loads) and leaves a 32-byte slot {key, fingerprint, record start, head / id / seq lengths};
+// Same skeleton as k_stats_tile.cu (tile_common.cuh).  Every owned record is hashed from shared memory by four
+// lanes (XXH64 seed 0 = the reference's key, and FP64 for the 128-bit fingerprint, xxh64.cuh; 8-byte little-endian
+// words assembled from aligned 32-bit loads) and leaves a 32-byte slot {key, fingerprint, record start, head / id / seq lengths};
 // k_rmdup_tile_compact turns the per-tile slot lists into the dense per-record arrays (keys, fingerprints and the
 // RecArrays of the general path), after which table insert / resolve / k_emit_contig run unchanged.
 // Records outside the grammar ("+name" lines, multi-line, longer than the halo, --ignore-case) -> general path.
@@ -21,7 +21,6 @@ namespace k {
 namespace rt {
 typedef tile::Geo<512, 3, 3, 2, 3072> G;
 constexpr u32 RCAP = 192;  // record slots per tile (20 KiB tile: records of >= 107 bytes on average)
-constexpr u64 kSeedB = 0x9E3779B97F4A7C15ull;
 
 struct Smem {
   u8 in[G::NSTAGE][G::STAGE];
@@ -177,26 +176,63 @@ __global__ void __launch_bounds__(rt::G::NT, rt::G::CTAS) k_rmdup_tile(RmdupTile
     if (bad) {
       if (tid == 0) atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
     } else {
-      // ---- one thread per record: subject hash pair + slot
-      for (u32 r = tid; r < n_own; r += NT) {
-        const u32 k = sm.r_line[r];
-        const u32 p0 = sm.ls[k] & 0x7fffu, l1 = sm.ls[k + 1] & 0x7fffu, l2 = sm.ls[k + 2] & 0x7fffu;
-        const u32 hl = l1 - 1 - (p0 + 1), sl = l2 - 1 - l1;
-        const u32 idl = rt_id_len(d + p0 + 1, hl);
-        u32 so = l1, slen = sl;
-        if (a.subject == 1) { so = p0 + 1; slen = hl; }
-        else if (a.subject == 2) { so = p0 + 1; slen = idl; }
-        u64 ka = 0, kb2 = 0;
-        if (a.subject >= 0) xxh64_pair(GetWords{d, so}, slen, 0, kSeedB, ka, kb2, true);
-        RmdupSlot sl_;
-        sl_.key = ka;
-        sl_.fp = kb2;
-        sl_.rec_start = t0 + p0;
-        sl_.hl = (u16)hl;
-        sl_.idl = (u16)idl;
-        sl_.sl = (u16)sl;
-        sl_.pad = 0;
-        a.slots[(size_t)tile * RCAP + r] = sl_;
+      // ---- four lanes per record: lane i takes word i of every 32-byte stripe of the subject (XXH64's four
+      // accumulators are independent, FP64's lanes likewise); the tail and the final mix are done by all four alike
+      const u32 gl = tid & 3u, g0lane = lane & ~3u;
+      for (u32 rb = 0; rb < n_own; rb += NT / 4) {  // uniform trip count
+        const u32 r = rb + (tid >> 2);
+        const bool act = r < n_own;
+        u32 p0 = 0, hl = 0, sl = 0, idl = 0, so = 0, slen = 0;
+        if (act) {
+          const u32 k = sm.r_line[r];
+          p0 = sm.ls[k] & 0x7fffu;
+          const u32 l1 = sm.ls[k + 1] & 0x7fffu, l2 = sm.ls[k + 2] & 0x7fffu;
+          hl = l1 - 1 - (p0 + 1);
+          sl = l2 - 1 - l1;
+          so = l1;
+          slen = sl;
+          if (a.subject == 1) { so = p0 + 1; slen = hl; }
+          else if (a.subject == 2) { idl = rt_id_len(d + p0 + 1, hl); so = p0 + 1; slen = idl; }
+          if (a.subject < 0) slen = 0;
+        }
+        const GetWords gw{d, so};
+        u64 v = gl == 0 ? XXP1 + XXP2 : (gl == 1 ? XXP2 : (gl == 2 ? 0ull : 0ull - XXP1));
+        u64 g = fp_lane_init(gl);
+        const u32 ns = slen >> 5;
+        for (u32 s2 = 0; s2 < ns; s2++) {
+          const u64 w = xx_rd64(gw, 32u * s2 + 8u * gl);
+          v = xx_round(v, w);
+          g = fp_lane_step(g, w);
+        }
+        const u64 v1 = __shfl_sync(0xffffffffu, v, g0lane), v2 = __shfl_sync(0xffffffffu, v, g0lane + 1u);
+        const u64 v3 = __shfl_sync(0xffffffffu, v, g0lane + 2u), v4 = __shfl_sync(0xffffffffu, v, g0lane + 3u);
+        const u64 f0 = __shfl_sync(0xffffffffu, g, g0lane), f1 = __shfl_sync(0xffffffffu, g, g0lane + 1u);
+        const u64 f2 = __shfl_sync(0xffffffffu, g, g0lane + 2u), f3 = __shfl_sync(0xffffffffu, g, g0lane + 3u);
+        u64 h;
+        if (ns) {
+          h = xx_rotl(v1, 1) + xx_rotl(v2, 7) + xx_rotl(v3, 12) + xx_rotl(v4, 18);
+          h = xx_merge(h, v1);
+          h = xx_merge(h, v2);
+          h = xx_merge(h, v3);
+          h = xx_merge(h, v4);
+        } else {
+          h = XXP5;
+        }
+        h += (u64)slen;
+        u64 t = XXP5;
+        key_fp_tail(gw, 32u * ns, slen, h, t);
+        if (act && gl == 0) {
+          if (a.subject != 2) idl = rt_id_len(d + p0 + 1, hl);
+          RmdupSlot sl_;
+          sl_.key = a.subject >= 0 ? xx_avalanche(h) : 0;
+          sl_.fp = a.subject >= 0 ? fp_finish(f0, f1, f2, f3, t, slen) : 0;
+          sl_.rec_start = t0 + p0;
+          sl_.hl = (u16)hl;
+          sl_.idl = (u16)idl;
+          sl_.sl = (u16)sl;
+          sl_.pad = 0;
+          a.slots[(size_t)tile * RCAP + r] = sl_;
+        }
       }
       if (tid == 0) a.tile_cnt[tile] = n_own;
     }

@@ -23,6 +23,7 @@ struct Engine::RmdupState {
   // subject slices of the block in flight
   const u8 *sv_base = nullptr;
   const u32 *sv_off = nullptr, *sv_len = nullptr;
+  u64 sv_limit = 0;
   bool block_ready = false;
   // rmdup -d / -D, accumulated on the host between Before and After (bigseqkit-lib/rmdup.go:102-103,224-238)
   std::string dup_seqs;                        // removed records, Record.Format(LineWidth), input order

@@ -14,12 +14,12 @@
 
 namespace bsk {
 
-static const u64 kSeedB = 0x9E3779B97F4A7C15ull;
 static const u64 kNoFirst = ~0ull;
 
 struct SubjectViews {
   const u8 *base;
   const u32 *off, *len;
+  u64 limit;  // readable bytes of base (word loads stop there)
 };
 
 struct GetRaw {
@@ -41,8 +41,8 @@ __global__ void k_rmdup_hash(SubjectViews sv, u32 n_rec, int ignore_case, u64 *_
   const u8 *p = sv.base + sv.off[r];
   const u32 len = sv.len[r];
   u64 a, b;
-  if (ignore_case) xxh64_pair(GetLower{p}, len, 0, kSeedB, a, b, true);
-  else xxh64_pair(GetRaw{p}, len, 0, kSeedB, a, b, true);
+  if (ignore_case) xxh64_key_fp(GetLower{p}, len, a, b);
+  else xxh64_key_fp(GetRaw{p}, len, a, b);
   keys[r] = a;
   fps[r] = b;
 }
@@ -87,14 +87,32 @@ __global__ void k_table_insert(const u64 *__restrict__ keys, u64 n, u64 g_base, 
 __device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32 b, int ignore_case) {
   const u32 la = sv.len[a];
   if (la != sv.len[b]) return false;
-  const u8 *pa = sv.base + sv.off[a], *pb = sv.base + sv.off[b];
+  const u32 oa = sv.off[a], ob = sv.off[b];
+  const u8 *pa = sv.base + oa, *pb = sv.base + ob;
   if (ignore_case) {
     GetLower ga{pa}, gb{pb};
     for (u32 i = 0; i < la; i++)
       if (ga(i) != gb(i)) return false;
-  } else {
+    return true;
+  }
+  const u64 top = (u64)(oa > ob ? oa : ob) + la + 8u;
+  if (top > sv.limit || (((size_t)sv.base) & 3u)) {  // too close to the end of the buffer for word loads
     for (u32 i = 0; i < la; i++)
       if (pa[i] != pb[i]) return false;
+    return true;
+  }
+  // four bytes per step: aligned 32-bit loads, funnel shifts resolve the two alignments
+  const u32 *wa = reinterpret_cast<const u32 *>(sv.base + (oa & ~3u)), *wb = reinterpret_cast<const u32 *>(sv.base + (ob & ~3u));
+  const u32 sa = (oa & 3u) * 8u, sb = (ob & 3u) * 8u;
+  u32 a0 = wa[0], b0 = wb[0];
+  const u32 nw = (la + 3u) >> 2;
+  for (u32 i = 0; i < nw; i++) {
+    const u32 a1 = wa[i + 1], b1 = wb[i + 1];
+    u32 x = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+    if (i + 1 == nw && (la & 3u)) x &= (1u << (8u * (la & 3u))) - 1u;
+    if (x) return false;
+    a0 = a1;
+    b0 = b1;
   }
   return true;
 }
@@ -173,9 +191,9 @@ static void hist_reserve(Engine::RmdupState *rm, u64 need, cudaStream_t s) {
 }
 
 static void table_reserve(Engine::RmdupState *rm, u64 total, cudaStream_t s, u64 &launches) {
-  if (rm->cap && !rm->dirty && total * 2 <= rm->cap) return;
+  if (rm->cap && !rm->dirty && total * 3 <= rm->cap * 2) return;  // load factor <= 2/3
   u64 cap = 1u << 12;
-  while (cap < total * 4) cap *= 2;
+  while (cap < total * 2) cap *= 2;
   if (cap > rm->alloc_cap) {  // device memory is kept across bsk_reset / partitions: only growth reallocates
     if (rm->table) cudaFree(rm->table);
     rm->table = nullptr;
@@ -217,18 +235,19 @@ int Engine::rmdup_hash_block() {
   const size_t R = (size_t)n_rec_ + 1;
   SubjectViews sv;
   if (o_.BySeq) {
-    sv = SubjectViews{views_.seqb, views_.seq_off, views_.seq_len};
+    sv = SubjectViews{views_.seqb, views_.seq_off, views_.seq_len, views_.seqb == in_ ? (u64)n_ : (u64)seq_space_};
   } else if (o_.ByName) {
-    sv = SubjectViews{in_, ra_.head_off, ra_.head_len};
+    sv = SubjectViews{in_, ra_.head_off, ra_.head_len, (u64)n_};
   } else {
     u32 *ids = b_id_.get<u32>(R * 2);
     k::id_desc(views_, o_.IDNCBI ? 1 : 0, ids, ids + R, nullptr, nullptr, stream);
     launches_++;
-    sv = SubjectViews{in_, ids, ids + R};
+    sv = SubjectViews{in_, ids, ids + R, (u64)n_};
   }
   rm_->sv_base = sv.base;
   rm_->sv_off = sv.off;
   rm_->sv_len = sv.len;
+  rm_->sv_limit = sv.limit;
   u64 *keys = b_op1_.get<u64>(R);
   u64 *fps = b_op2_.get<u64>(R);
   if (n_rec_) {
@@ -244,7 +263,7 @@ int Engine::rmdup_resolve_block(BlockOut &bo) {
   RmdupState *rm = rm_;
   const u64 g_base = rm->n_hist;
   u64 *keys = b_op1_.as<u64>(), *fps = b_op2_.as<u64>();
-  SubjectViews sv{rm->sv_base, rm->sv_off, rm->sv_len};
+  SubjectViews sv{rm->sv_base, rm->sv_off, rm->sv_len, rm->sv_limit};
   u8 *keep = b_keep_.get<u8>((size_t)n_rec_ + 1);
   const bool want_dup_seqs = !o_.DupSeqsFile.empty(), want_dup_num = !o_.DupNumFile.empty();
   u64 *first = want_dup_num ? b_op5_.get<u64>((size_t)n_rec_ + 1) : nullptr;
@@ -520,10 +539,14 @@ int Engine::op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only
   }
   if (!rm_) rm_ = new RmdupState();
   rm_->sv_base = d_in;
+  rm_->sv_limit = n;
   rm_->sv_off = subject == 0 ? ra_.seq_off : ra_.head_off;
   rm_->sv_len = subject == 0 ? ra_.seq_len : (subject == 1 ? ra_.head_len : ids + R);
   timings.fused_blocks++;
-  return rmdup_finish(bo, prepare_only);
+  contig_known_ = true;  // the tile kernel accepted the block: every record is printed exactly as it stands in the input
+  const int frc = rmdup_finish(bo, prepare_only);
+  contig_known_ = false;
+  return frc;
 }
 
 int Engine::rmdup_keys(const int64_t **keys, size_t *n) {

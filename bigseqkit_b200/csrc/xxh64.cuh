@@ -125,4 +125,58 @@ __host__ __device__ __forceinline__ void xxh64_pair(const Get &get, u32 len, u64
   hb = want_b ? xx_avalanche(g) : 0;
 }
 
+// ---- the 128-bit fingerprint of rmdup: {XXH64 seed 0 (the reference's key), FP64}.  FP64 is an independent 64-bit hash
+// of the same bytes built for cheap evaluation next to XXH64: four multiply-xor lanes over the 32-byte stripes (lane i
+// takes word i of every stripe, so four threads can share one subject) + a serial tail, folded with the length.
+static const u64 kFpSeed = 0x9E3779B97F4A7C15ull;
+__host__ __device__ __forceinline__ u64 fp_lane_init(u32 i) { return kFpSeed + (u64)i * XXP3; }
+__host__ __device__ __forceinline__ u64 fp_lane_step(u64 g, u64 w) { return xx_rotl((g ^ w) * XXP2, 29); }
+__host__ __device__ __forceinline__ u64 fp_finish(u64 g0, u64 g1, u64 g2, u64 g3, u64 t, u32 len) {
+  return xx_avalanche(g0 + xx_rotl(g1, 17) + xx_rotl(g2, 31) + xx_rotl(g3, 47) + t + (u64)len * XXP4);
+}
+// the bytes behind the last whole stripe (p .. len): XXH64's tail steps on h, FP64's on t
+template <class Get>
+__host__ __device__ __forceinline__ void key_fp_tail(const Get &get, u32 p, u32 len, u64 &h, u64 &t) {
+  for (; p + 8 <= len; p += 8) {
+    const u64 w = xx_rd64(get, p);
+    h ^= xx_round(0, w);
+    h = xx_rotl(h, 27) * XXP1 + XXP4;
+    t = xx_rotl((t ^ w) * XXP1, 27);
+  }
+  if (p + 4 <= len) {
+    const u64 w = xx_rd32(get, p);
+    h ^= w * XXP1;
+    h = xx_rotl(h, 23) * XXP2 + XXP3;
+    t = xx_rotl((t ^ w) * XXP2, 23);
+    p += 4;
+  }
+  for (; p < len; p++) {
+    const u64 c = get(p);
+    h ^= c * XXP5;
+    h = xx_rotl(h, 11) * XXP1;
+    t = xx_rotl((t ^ c) * XXP5, 11);
+  }
+}
+// one thread, one subject: key = XXH64 seed 0, fp = FP64
+template <class Get>
+__host__ __device__ __forceinline__ void xxh64_key_fp(const Get &get, u32 len, u64 &key, u64 &fp) {
+  XxState a;
+  a.init(0);
+  u64 g0 = fp_lane_init(0), g1 = fp_lane_init(1), g2 = fp_lane_init(2), g3 = fp_lane_init(3);
+  u32 p = 0;
+  const bool stripes = len >= 32;
+  for (; p + 32 <= len; p += 32) {
+    const u64 w0 = xx_rd64(get, p), w1 = xx_rd64(get, p + 8), w2 = xx_rd64(get, p + 16), w3 = xx_rd64(get, p + 24);
+    a.stripe(w0, w1, w2, w3);
+    g0 = fp_lane_step(g0, w0);
+    g1 = fp_lane_step(g1, w1);
+    g2 = fp_lane_step(g2, w2);
+    g3 = fp_lane_step(g3, w3);
+  }
+  u64 h = a.converge(stripes) + (u64)len, t = XXP5;
+  key_fp_tail(get, p, len, h, t);
+  key = xx_avalanche(h);
+  fp = fp_finish(g0, g1, g2, g3, t, len);
+}
+
 }  // namespace bsk
