@@ -72,6 +72,16 @@ static inline int __syncthreads_or(int p) {
   emu::sync_block();
   return r;
 }
+static inline int __syncthreads_count(int p) {
+  static std::atomic<int> cnt{0};  // one block runs at a time in the emulator
+  if (p) cnt.fetch_add(1);
+  emu::sync_block();
+  const int r = cnt.load();
+  emu::sync_block();
+  if (emu::t_threadIdx.x == 0) cnt.store(0);
+  emu::sync_block();
+  return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }

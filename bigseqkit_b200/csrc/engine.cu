@@ -6,9 +6,19 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "op_state.h"
 #include "prims.h"
 
 namespace bsk {
+
+// per-operator state that outlives a block (rmdup key table and history, locate / grep pattern tables)
+void Engine::free_op_state() {
+  rmdup_state_free(rm_);
+  rm_ = nullptr;
+  delete pats_;
+  pats_ = nullptr;
+}
+void Engine::reset_op_state() { rmdup_state_reset(rm_); }
 
 Engine::Engine(Op op, const Opts &o, int device) : op_(op), o_(o), device_(device) {
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));

@@ -164,8 +164,7 @@ class Engine {
 
   int process_block(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo);
   int op_seq(BlockOut &bo);
-  // single-pass tile kernel for short records (k_fused.cu); returns kFusedFallback when the block
-  // must take the general path instead
+  // single-pass tile kernels for short records (ops_tile.cu); kFusedFallback = the block must take the general path
   static const int kFusedFallback = 1000;
   bool fused_ok_ = true;
   bool inplace_ok_ = true;
@@ -182,7 +181,6 @@ class Engine {
   u32 first_seq_len_ = 0;  // sequence length of the partition's first record (lane-group choice of the tile kernels)
   DevBuf b_tile_cnt_, b_tile_base_, b_slots_;
   int first_record_alphabet(const u8 *d_in, u32 n, bool &fastq, bool &ok, bool long_ok = false);
-  DevBuf b_tiles_;
   PinnedBuf h_probe_;
   int op_stats(BlockOut &bo);
   int op_rmdup(BlockOut &bo, bool prepare_only);

@@ -99,20 +99,13 @@ void remove_gaps(RecViews v, const u8 *gap, u8 *seq_out, u8 *qual_out, u32 *new_
 void seq_filter(RecViews v, int min_len, int max_len, double min_qual, double max_qual, const double *qual_pow,
                 u8 *keep, cudaStream_t s);
 
-// ---- single-pass tile kernels for short records (k_fused.cu)
-size_t fused_smem_bytes();
-size_t fused_tile_state_bytes(u32 n);
-u32 fused_max_records(u32 n);
-void seq_fused(const u8 *in, u32 n, u8 *out, u64 *elem_off, const u8 *lut, void *tile_state, u32 *ticket, DevStatus *st,
-               EmitCfg cfg, int only_id, int fastq, int min_len, int max_len, cudaStream_t s);
-
 // ---- FASTQ same-layout in-place kernel (k_fastq_inplace.cu): TMA-staged, no inter-CTA dependency
-u32 fastq_inplace_tiles(u32 n, int variant);
+u32 fastq_inplace_tiles(u32 n);
 u32 fastq_inplace_slot_stride();
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
-                   int use_lut, int group, u32 max_seg, u32 scan_halo, int variant, int n_sm, cudaStream_t s);
-void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, int variant,
-                       u64 cap, const DevStatus *st, cudaStream_t s);
+                   int use_lut, int group, u32 max_seg, u32 scan_halo, int n_sm, cudaStream_t s);
+void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, u64 cap,
+                       const DevStatus *st, cudaStream_t s);
 
 // ---- stats on short records in one streaming pass (k_stats_tile.cu)
 u32 stats_tile_bins();

@@ -1,4 +1,5 @@
-// ops_fused.cu -- host side of the single-pass tile path (k_fused.cu) for `seq` on short records.
+// ops_tile.cu -- host side of the single-pass tile kernels for short records: `seq` on 4-line FASTQ in same-layout
+// mode (k_fastq_inplace.cu) and `stats` (k_stats_tile.cu); everything they decline goes to the general path.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -147,54 +148,10 @@ int Engine::op_seq_fused(const u8 *d_in, u32 n, BlockOut &bo) {
     }
     reset_status();
   }
-  // Everything else goes to the general path: with the tile index and the window-based formatter it is about twice
-  // as fast as k_seq_fused below (3.9 vs 6.8 ms per GiB of FASTQ with a length filter, 4.3 vs 8.9 ms per GiB of
-  // wrapped FASTA reverse-complemented).  k_seq_fused stays selectable (BSK_FORCE_FUSED) and parity-tested.
-  if (getenv("BSK_FORCE_FUSED") == nullptr) {
-    alphabet_ = saved_alpha;
-    alphabet_known_ = saved_known;
-    return kFusedFallback;
-  }
-  // output can only grow through FASTA line wrapping: one '\n' per `width` bases, plus a final newline
-  size_t bound = (size_t)n + 64;
-  if (!fastq && cfg.width) bound += (size_t)n / cfg.width;
-  u8 *out = b_out_.get<u8>(bound);
-  u64 *elem = nullptr;
-  if (want_elem_off) elem = b_elem_.get<u64>((size_t)k::fused_max_records(n) + 2);
-  const size_t ts_bytes = k::fused_tile_state_bytes(n);
-  u8 *ts = b_tiles_.get<u8>(ts_bytes + 64);
-  BSK_CUDA(cudaMemsetAsync(ts, 0, ts_bytes + 64, stream));
-  u32 *ticket = reinterpret_cast<u32 *>(ts + ts_bytes);
-  main_begin();
-  k::seq_fused(d_in, n, out, elem, t_lut_, ts, ticket, d_status_, cfg, o_.OnlyId ? 1 : 0, fastq ? 1 : 0, o_.MinLen, o_.MaxLen,
-               stream);
-  main_end();
-  launches_++;
-  fetch_status();
-  if (h_status_->counters[0]) {  // some tile could not be handled: take the general path for the whole block
-    alphabet_ = saved_alpha;
-    alphabet_known_ = saved_known;
-    main_timed_ = false;
-    timings.main_launches--;
-    return kFusedFallback;
-  }
-  const u64 total = h_status_->counters[1], nrec = h_status_->counters[2], kept = h_status_->counters[3];
-  if (elem) {
-    u8 *hs = h_small_.as<u8>();
-    memcpy(hs, &total, 8);
-    BSK_CUDA(cudaMemcpyAsync(elem + kept, hs, 8, cudaMemcpyHostToDevice, stream));
-  }
-  fastq_ = fastq;
-  if (first_block_) part_fastq_ = fastq;
-  n_rec_ = (u32)nrec;
-  bo.d_data = out;
-  bo.n = total;
-  bo.d_elem_off = elem;
-  bo.n_elem = kept;
-  bo.n_rec = nrec;
-  if (nrec) any_record_ = true;
-  timings.fused_blocks++;
-  return BSK_OK;
+  // Everything else goes to the general path (tile index + window-based formatter).
+  alphabet_ = saved_alpha;
+  alphabet_known_ = saved_known;
+  return kFusedFallback;
 }
 
 // `stats` on short records: one streaming kernel (k_stats_tile.cu), histogram + counters merged on the host.
@@ -280,23 +237,21 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
     BSK_CUDA(cudaGetDeviceProperties(&prop, dev));
     n_sm_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
   }
-  int variant = 3;  // CTA shapes of k_fastq_inplace.cu (fq::CfgA..F); 3 = 512 threads x 3 CTAs / SM, 2-stage ring (measured best)
-  if (const char *e = getenv("BSK_FQ_VARIANT")) variant = atoi(e) >= 0 && atoi(e) <= 6 ? atoi(e) : 0;
-  const u32 n_tiles = k::fastq_inplace_tiles(n, variant);
+  const u32 n_tiles = k::fastq_inplace_tiles(n);
   u8 *out = b_out_.get<u8>((size_t)n + 64);
   u32 *tile_cnt = b_tile_cnt_.get<u32>((size_t)n_tiles + 1);
   u16 *slots = b_slots_.get<u16>((size_t)n_tiles * k::fastq_inplace_slot_stride());
   BSK_CUDA(cudaMemsetAsync(tile_cnt, 0, ((size_t)n_tiles + 1) * 4, stream));
   BSK_CUDA(cudaMemsetAsync(&d_status_->counters[4], 0xff, 8, stream));
   main_begin();
-  // lanes per record: 8 lanes x 8 words hold segments up to ~256 B (reads), 32 x 4 up to ~512 B; longer ones take
+  // lanes per record: 8 lanes x 8 words hold segments up to 250 B (reads), 32 x 4 up to ~500 B; longer ones take
   // the byte-pair path inside the kernel
   int group = first_seq_len_ <= 250 ? 8 : 32;
-  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 4 ? 4 : atoi(e) == 8 ? 8 : atoi(e) == 16 ? 16 : 32;
+  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : 32;  // test hook: both lane groupings on any input
   // the newline scan first covers the halo as far as two records like the first one reach
   const u32 scan_halo = 2u * first_rec_bytes_ + 64u;
   k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group,
-                   first_seq_len_, scan_halo, variant, n_sm_, stream);
+                   first_seq_len_, scan_halo, n_sm_, stream);
   main_end();
   launches_++;
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
@@ -309,7 +264,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
     cap = (u64)n / (first_rec_bytes_ > 16 ? first_rec_bytes_ / 2 : 8) + 1024;
     if (b_elem_.cap / 8 > cap) cap = b_elem_.cap / 8;
     elem = b_elem_.get<u64>((size_t)cap);
-    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, cap, d_status_, stream);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, cap, d_status_, stream);
     launches_++;
   }
   u8 *hs = h_small_.as<u8>();
@@ -332,7 +287,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   if (want_elem_off && nrec + 1 > cap) {  // more records than the first one suggested
     cap = nrec + 2;
     elem = b_elem_.get<u64>((size_t)cap);
-    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, variant, cap, d_status_, stream);
+    k::fastq_elem_expand(tile_cnt, tile_base, slots, elem, n_tiles, cap, d_status_, stream);
     launches_++;
   }
   fastq_ = fastq;

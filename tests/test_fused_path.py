@@ -1,5 +1,6 @@
-"""The single-pass tile path (k_fused.cu) for short records: parity with the oracle on inputs that span
-many tiles, and clean fall-back to the general path for everything the tile scheme cannot represent."""
+"""The single-pass tile kernels for short records (k_fastq_inplace.cu; the general path behind them): parity with the
+oracle on inputs that span many tiles, and clean fall-back to the general path for everything the tile scheme cannot
+represent."""
 import random
 
 import pytest
@@ -45,9 +46,7 @@ def big_inputs():
 
 
 @pytest.mark.parametrize("opts", OPTS, ids=lambda o: str(o)[:60])
-def test_fused_parity_many_tiles(lib, opts, monkeypatch):
-    # plain re-formatting normally goes to the general path (byte-range compaction is faster); force the tile kernel
-    monkeypatch.setenv("BSK_FORCE_FUSED", "1")
+def test_parity_many_tiles(lib, opts):
     for name, data in big_inputs().items():
         try:
             exp = oracle.seq(data, opts)
@@ -56,7 +55,6 @@ def test_fused_parity_many_tiles(lib, opts, monkeypatch):
         r, t = run(lib, data, opts)
         assert r.data == exp[0], (name, opts)
         assert list(r.elem_off) == exp[1], (name, opts)
-        assert t["fused_blocks"] == 1, (name, opts, "expected the single-pass tile path")
 
 
 def test_plain_formatting_takes_the_general_path(lib):
@@ -201,32 +199,24 @@ def test_inplace_leaves_other_grammars_to_the_general_paths(lib, name):
         assert r.data == exp[0] and list(r.elem_off) == exp[1], name
 
 
-def test_tile_path_owns_records_that_start_on_a_tile_boundary(lib, monkeypatch):
-    # regression: a record whose first byte is the first byte of a 16 KiB tile was dropped by k_seq_fused
-    monkeypatch.setenv("BSK_NO_INPLACE", "1")
-    monkeypatch.setenv("BSK_FORCE_FUSED", "1")
+def test_records_that_start_on_a_tile_boundary(lib):
+    # 64-byte records: every tile boundary (20 KiB tiles here, 16 KiB tiles of the FASTA index) is a record start
     data = _fixed_fastq(2000, 8, 25, 41)
     for opts in ({"Reverse": True, "Complement": True}, {"MinLen": 5}, {"Name": True}):
         exp = oracle.seq(data, opts)
         r, t = run(lib, data, opts)
         assert r.data == exp[0] and list(r.elem_off) == exp[1]
-        assert t["fused_blocks"] == 1 and t["kernel_launches"] == 1
     fa = b"".join(b">%05d\n%s\n" % (i, b"ACGTACGTAC" * 5 + b"ACGTAC") for i in range(2000))  # 64-byte FASTA records
     exp = oracle.seq(fa, {"Complement": True})
     r, t = run(lib, fa, {"Complement": True})
-    assert r.data == exp[0] and list(r.elem_off) == exp[1] and t["fused_blocks"] == 1
+    assert r.data == exp[0] and list(r.elem_off) == exp[1]
 
 
-@pytest.mark.parametrize("variant", ["0", "1", "2", "3", "4", "5", "6"])
-@pytest.mark.parametrize("group", ["4", "8", "16", "32"])
-def test_inplace_lane_group_variants(lib, monkeypatch, group, variant):
-    # every combination runs on the GPU; the host emulator (slow: OS threads) takes a covering subset
-    if lib.path.endswith("libbsk_emu.so") and (group, variant) not in {("8", "3"), ("4", "0"), ("16", "1"), ("32", "2"), ("8", "4"),
-                                                                      ("16", "5"), ("32", "6")}:
-        pytest.skip("covered on the GPU")
+@pytest.mark.parametrize("group", ["8", "32"])
+@pytest.mark.parametrize("opts", [{"Reverse": True, "Complement": True}, {"Reverse": True}, {"Complement": True}], ids=str)
+def test_inplace_lane_groups(lib, monkeypatch, group, opts):
+    # both lane groupings of the in-place transform on every input (the library picks one from the first record)
     monkeypatch.setenv("BSK_FQ_GROUP", group)
-    monkeypatch.setenv("BSK_FQ_VARIANT", variant)
-    opts = {"Reverse": True, "Complement": True}
     for name in ("reads150", "len250", "len251_to_600", "rec64_tile_aligned", "empty_seq_and_header", "short_then_long",
                  "no_final_newline", "rec48_many_lines"):
         data = inplace_inputs()[name]
