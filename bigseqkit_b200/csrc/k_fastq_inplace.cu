@@ -72,11 +72,11 @@ struct FqInplaceArgs {
   u32 scan_halo;   // bytes of the halo the newline scan covers on its first attempt (multiple of 16, <= H)
 };
 
-// flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value
+// flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value.  (x | 0x80) - 1 keeps bit 7 of a
+// byte unless its low seven bits are zero, and never borrows across bytes; bit 7 of w ^ '\n' is bit 7 of w.
 __device__ __forceinline__ u32 nl_flags(u32 w) {
-  const u32 x = w ^ 0x0a0a0a0au;
-  const u32 y = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-  return ~(y | x) & 0x80808080u;
+  const u32 t = ((w ^ 0x0a0a0a0au) | 0x80808080u) - 0x01010101u;
+  return ~(t | w) & 0x80808080u;
 }
 
 // four table look-ups.  The table sits on a 256-byte boundary of shared memory, so the address of entry b is the table
@@ -490,18 +490,25 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
 
     // ---- in-place transform
     if (n_own && (a.reverse || a.use_lut)) {
-      if (a.group == 8) {
+      if (a.group == 4) {
+        transform_tile<4, 10>(sm, d, kmin, n_own, a.reverse, a.use_lut);
+      } else if (a.group == 8) {
         if (a.wpl <= 5) transform_tile<8, 5>(sm, d, kmin, n_own, a.reverse, a.use_lut);
         else transform_tile<8, 8>(sm, d, kmin, n_own, a.reverse, a.use_lut);
       } else {
         transform_tile<32, 4>(sm, d, kmin, n_own, a.reverse, a.use_lut);
       }
     }
-    tma::fence_proxy_async();
-    __syncthreads();
-
     // ---- owned byte range [lo, hi) -> out, same offsets: bulk store of the aligned body, ragged ends by warp 0.
     // Owned records are contiguous: from the first owned record line to the line after the last one.
+    // Only warp 0 waits for the transform to finish; the other warps arrive and go on to scan the next tile (other
+    // stage; nothing of this tile is overwritten before the next full barrier, which warp 0 joins after the store).
+    tma::fence_proxy_async();
+    if (warp != 0) {
+      tma::named_arrive(1, NT);
+    } else {
+      tma::named_sync(1, NT);
+    }
     if (warp == 0 && n_own > 0) {
       const u32 lo = sm.ls[kmin];
       const u32 hi = sm.ls[kmin + 4u * n_own];  // start of the next record == one past the '\n' that ends the last owned one
@@ -562,7 +569,7 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   a.n_tiles = fastq_inplace_tiles(n);
   a.reverse = reverse;
   a.use_lut = use_lut;
-  a.group = group == 8 ? 8 : 32;
+  a.group = group == 8 ? 8 : (group == 4 ? 4 : 32);
   a.wpl = max_seg <= 154 ? 5 : 8;
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > fq::H ? fq::H : scan_halo);

@@ -22,11 +22,13 @@ constexpr u32 HB = 4224;  // histogram bins: a record (and so its sequence) is s
 typedef tile::Geo<512, 3, 3, 2, 3072> G;
 constexpr u32 ICAP = G::LCAP;  // work items (sequence / quality lines) per tile
 
+// -a needs the work-item list (12 KiB): 2 CTAs / SM; without it 3 CTAs / SM fit
+template <bool ALL>
 struct Smem {
   u8 in[G::NSTAGE][G::STAGE];
   u64 full[G::NSTAGE];
   u16 ls[G::LCAP + 8];
-  u32 item[ICAP];     // a (15 bits) | len (15 bits) << 15 | kind << 30   (kind 1 = quality line)
+  u32 item[ALL ? ICAP : 1];  // a (15 bits) | len (15 bits) << 15 | kind << 30   (kind 1 = quality line)
   u32 hist[HB];
   u32 wtot[G::NWARP];
   u32 bad, rescan, n_item, n_rec;
@@ -53,8 +55,10 @@ __device__ __forceinline__ u32 count_ge4(u32 w, u32 c4) {
   return (u32)__popc((t | w) & 0x80808080u);
 }
 
-__global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTileArgs a) {
+template <bool ALL>
+__global__ void __launch_bounds__(st::G::NT, ALL ? 2 : 3) k_stats_tile(StatsTileArgs a) {
   using namespace st;
+  typedef st::Smem<ALL> Smem;
   using tile::H;
   using tile::PRE;
   constexpr u32 NT = G::NT, T = G::T, NSTAGE = G::NSTAGE;
@@ -133,10 +137,23 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
       if (r.st == 0 && r.slen >= HB) r.st = 2;
       return r;
     };
-    // a complete owned record: length -> histogram; with -a its sequence / quality lines -> work items
-    auto commit = [&](u32 k, const Ev &r) {
-      atomicAdd(&sm.hist[r.slen], 1u);
-      if (!a.all || !r.slen) return;
+    // complete owned records of a warp: lengths -> histogram.  Reads of one length all hit the same bin, which a
+    // shared-memory atomic would serialise lane by lane: when every record of the warp has the length of the first
+    // one, a single lane adds the count.  Every lane of the warp calls it (valid = this lane has a record).
+    auto commit_hist = [&](bool valid, u32 slen) {
+      const u32 bal = __ballot_sync(0xffffffffu, valid);
+      if (!bal) return;
+      const u32 leader = (u32)__ffs((int)bal) - 1u;
+      const u32 first = __shfl_sync(0xffffffffu, slen, (int)leader);
+      if (__all_sync(0xffffffffu, !valid || slen == first)) {
+        if (lane == leader) atomicAdd(&sm.hist[first], (u32)__popc(bal));
+      } else if (valid) {
+        atomicAdd(&sm.hist[slen], 1u);
+      }
+    };
+    // with -a the sequence / quality lines of a complete owned record become work items
+    auto commit_items = [&](u32 k, const Ev &r) {
+      if (!ALL || !r.slen) return;
       if (fq) {
         const u32 i0 = atomicAdd(&sm.n_item, 2u);
         if (i0 + 2 <= ICAP) {
@@ -175,14 +192,18 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
       for (u32 kb = 0; kb <= n_lines; kb += NT) {  // one trip unless direct
         if (kb + warp * 32u > n_lines) continue;    // warp-uniform
         const Ev r = evaluate(kb + tid, n_lines, slim);
+        const bool done = r.own && r.st == 0;
         if (r.own) {
           if (r.st == 1) sm.rescan = 1;
           else if (r.st == 2) sm.bad = 1;
-          else if (direct) commit(kb + tid, r);
         }
-        if (!direct) mine = r;
-        const u32 bal = __ballot_sync(0xffffffffu, r.own && r.st == 0);
-        n_new += (u32)__popc(bal);
+        if (direct) {
+          commit_hist(done, r.slen);
+          if (ALL && done) commit_items(kb + tid, r);
+        } else {
+          mine = r;
+        }
+        n_new += (u32)__popc(__ballot_sync(0xffffffffu, done));
       }
       __syncthreads();
       bad = sm.bad != 0 || (tile == 0 && !(sm.ls[0] & 0x8000u));
@@ -192,7 +213,11 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
         __syncthreads();  // everybody has read the flags before thread 0 clears them again
         continue;
       }
-      if (!direct && mine.own) commit(tid, mine);
+      if (!direct) {  // (one trip above: n_lines < NT)
+        const bool done = mine.own && mine.st == 0;
+        commit_hist(done, mine.slen);
+        if (ALL && done) commit_items(tid, mine);
+      }
       if (lane == 0 && n_new) atomicAdd(&sm.n_rec, n_new);
       if (!direct) {
         __syncthreads();  // work items pushed by commit()
@@ -202,7 +227,7 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
     }
     if (bad) {
       if (tid == 0) atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
-    } else if (a.all) {
+    } else if (ALL) {
       // ---- work items: 8 lanes per line, 4 bytes per lane and step
       const u32 n_item = sm.n_item;
       const u32 g = tid >> 3, gl = tid & 7u;
@@ -245,7 +270,7 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
     }
   }
   // ---- fold the CTA's results into the global ones
-  if (a.all) {
+  if (ALL) {
     for (int off = 16; off > 0; off >>= 1) {
       q20 += __shfl_xor_sync(0xffffffffu, q20, off);
       q30 += __shfl_xor_sync(0xffffffffu, q30, off);
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(st::G::NT, st::G::CTAS) k_stats_tile(StatsTile
   }
   if (tid == 0) {
     atomicAdd((unsigned long long *)&a.st->counters[5], (unsigned long long)sm.n_rec);
-    if (a.all) {
+    if (ALL) {
       atomicAdd((unsigned long long *)&a.st->counters[1], sm.acc[0]);
       atomicAdd((unsigned long long *)&a.st->counters[2], sm.acc[1]);
       atomicAdd((unsigned long long *)&a.st->counters[3], sm.acc[2]);
@@ -292,21 +317,24 @@ void stats_tile(const u8 *in, u32 n, u64 *hist, DevStatus *st, int fastq, int al
     if (gap_letters[i] >= 0x40) a.gap_below_40 = 0;
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > tile::H ? tile::H : scan_halo);
-  const size_t smem = sizeof(st::Smem) + 16;
-#ifndef BSK_EMU
-  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(k_stats_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set[dev] = true;
-  }
-#endif
-  u32 grid = (u32)n_sm * st::G::CTAS;
+  const int ctas = all ? 2 : 3;
+  u32 grid = (u32)n_sm * ctas;
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid == 0) return;
-  BSK_LAUNCH(k_stats_tile, grid, st::G::NT, smem, s, a);
+  const size_t smem = (all ? sizeof(st::Smem<true>) : sizeof(st::Smem<false>)) + 16;
+#ifndef BSK_EMU
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64][2] = {{false, false}};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev][all ? 1 : 0]) {
+    if (all) cudaFuncSetAttribute(k_stats_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(k_stats_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set[dev][all ? 1 : 0] = true;
+  }
+#endif
+  if (all) BSK_LAUNCH(k_stats_tile<true>, grid, st::G::NT, smem, s, a);
+  else BSK_LAUNCH(k_stats_tile<false>, grid, st::G::NT, smem, s, a);
 }
 
 }  // namespace k

@@ -247,7 +247,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
   // lanes per record: 8 lanes x 8 words hold segments up to 250 B (reads), 32 x 4 up to ~500 B; longer ones take
   // the byte-pair path inside the kernel
   int group = first_seq_len_ <= 250 ? 8 : 32;
-  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : 32;  // test hook: both lane groupings on any input
+  if (const char *e = getenv("BSK_FQ_GROUP")) group = atoi(e) == 8 ? 8 : (atoi(e) == 4 ? 4 : 32);  // test hook: both lane groupings on any input
   // the newline scan first covers the halo as far as two records like the first one reach
   const u32 scan_halo = 2u * first_rec_bytes_ + 64u;
   k::fastq_inplace(d_in, n, out, t_lut_, tile_cnt, slots, d_status_, cfg.reverse ? 1 : 0, need_lut ? 1 : 0, group,

@@ -27,11 +27,11 @@ struct Geo {
   static_assert(T % 16 == 0 && STAGE % 16 == 0 && T + H < 32768 && NWARP <= 16 && (CPL == 3 || CPL == 4), "tile geometry");
 };
 
-// flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value
+// flags (0x80 per byte) of the bytes of w that equal '\n'; exact for every byte value.  (x | 0x80) - 1 keeps bit 7 of a
+// byte unless its low seven bits are zero, and never borrows across bytes; bit 7 of w ^ '\n' is bit 7 of w.
 __device__ __forceinline__ u32 nl_flags(u32 w) {
-  const u32 x = w ^ 0x0a0a0a0au;
-  const u32 y = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
-  return ~(y | x) & 0x80808080u;
+  const u32 t = ((w ^ 0x0a0a0a0au) | 0x80808080u) - 0x01010101u;
+  return ~(t | w) & 0x80808080u;
 }
 
 // global byte range [g0, g1) that one bulk load brings for `tile` (whole 16-byte chunks of the file only)

@@ -60,6 +60,10 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // all bulk stores of this thread are complete
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// split CTA barrier (named barrier `id`, `count` threads): producers arrive and go on, the consumer waits for all of them
+__device__ __forceinline__ void named_arrive(u32 id, u32 count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(u32 id, u32 count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 #else  // ---- emulator
 static inline void mbar_init(u64 *bar, u32) { __atomic_store_n(bar, 0ull, __ATOMIC_SEQ_CST); }
 static inline void fence_barrier_init() {}
@@ -77,6 +81,8 @@ static inline void bulk_store(void *gdst, const void *smem_src, u32 bytes) { mem
 static inline void bulk_commit() {}
 static inline void bulk_wait_read() {}
 static inline void bulk_wait_all() {}
+static inline void named_arrive(u32, u32) { __syncthreads(); }  // no overlap in the emulator: both sides meet at a full barrier
+static inline void named_sync(u32, u32) { __syncthreads(); }
 #endif
 
 }  // namespace tma
