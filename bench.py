@@ -78,7 +78,7 @@ def workloads(block_mib):
                       "translate --frame 6, FASTA CDS 300-3000 bp wrapped at 60 (BASELINE configs[4])", "k_translate"),
         "locate": ("Locate", {"Pattern": panel()}, lambda b, r: synth.native_contigs(min(blk, 256 << 20), seed=4 + r, out=b), "locate",
                    "locate, 1000 x 12-mer panel, FASTA contigs log-uniform 1 kb - 5 Mb wrapped at 60 (BASELINE configs[3]; "
-                   "256 MiB block: the reference algorithm the oracle restates makes 2000 passes per contig)", "k_match"),
+                   "256 MiB block: the reference algorithm the oracle restates makes 2000 passes per contig)", "k_locate_tile"),
     }
 
 

@@ -168,72 +168,6 @@ int bsk_shard_bounds(const char *path, int n_shards, uint64_t *bounds) {
   return BSK_OK;
 }
 
-// pread / pwrite of one byte range by several threads: a single stream reads the page cache at memcpy speed of one
-// core, far below what the H2D pipeline takes (the step either side of every kernel)
-static bool par_io(int fd, unsigned char *buf, uint64_t len, uint64_t off, bool write) {
-  if (len == 0) return true;
-  const uint64_t kMinChunk = 8ull << 20;
-  unsigned hw = std::thread::hardware_concurrency();
-  if (hw == 0) hw = 1;
-  if (const char *e = getenv("BSK_IO_THREADS")) { const int v = atoi(e); if (v > 0) hw = (unsigned)v; }
-  uint64_t nt = (len + kMinChunk - 1) / kMinChunk;
-  if (nt > hw) nt = hw;
-  if (nt > 16) nt = 16;
-  const uint64_t chunk = ((len + nt - 1) / nt + 4095) & ~4095ull;
-  std::atomic<bool> ok{true};
-  auto work = [&](uint64_t t) {
-    uint64_t p = t * chunk;
-    const uint64_t end = p + chunk < len ? p + chunk : len;
-    while (p < end) {
-      const ssize_t r = write ? pwrite(fd, buf + p, end - p, (off_t)(off + p)) : pread(fd, buf + p, end - p, (off_t)(off + p));
-      if (r <= 0) { ok = false; return; }
-      p += (uint64_t)r;
-    }
-  };
-  std::vector<std::thread> th;
-  for (uint64_t t = 1; t < nt; t++) th.emplace_back(work, t);
-  work(0);
-  for (auto &x : th) x.join();
-  return ok;
-}
-
-// Output side: pwrite()s to one file serialise on the inode lock, so the range is mapped and filled by several
-// threads instead (page allocation then runs in parallel); plain pwrite when the file cannot be mapped.
-static bool par_write(int fd, const unsigned char *buf, uint64_t len, uint64_t off) {
-  if (len == 0) return true;
-  struct stat sb;
-  const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
-  if (getenv("BSK_NO_MMAP_WRITE") == nullptr && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode)) {
-    const uint64_t need = off + len;
-    // grow by writing this range's own last byte: never shrinks a file that another rank has already extended
-    if ((uint64_t)sb.st_size >= need || pwrite(fd, buf + len - 1, 1, (off_t)(need - 1)) == 1) {
-      const uint64_t m0 = off & ~(page - 1);
-      void *m = mmap(nullptr, need - m0, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)m0);
-      if (m != MAP_FAILED) {
-        unsigned char *dst = (unsigned char *)m + (off - m0);
-        unsigned hw = std::thread::hardware_concurrency();
-        if (hw == 0) hw = 1;
-        if (const char *e = getenv("BSK_IO_THREADS")) { const int v = atoi(e); if (v > 0) hw = (unsigned)v; }
-        uint64_t nt = (len + (8ull << 20) - 1) / (8ull << 20);
-        if (nt > hw) nt = hw;
-        if (nt > 16) nt = 16;
-        const uint64_t chunk = ((len + nt - 1) / nt + page - 1) & ~(page - 1);
-        auto work = [&](uint64_t t) {
-          const uint64_t p = t * chunk;
-          if (p < len) memcpy(dst + p, buf + p, p + chunk < len ? chunk : len - p);
-        };
-        std::vector<std::thread> th;
-        for (uint64_t t = 1; t < nt; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto &x : th) x.join();
-        munmap(m, need - m0);
-        return true;
-      }
-    }
-  }
-  return par_io(fd, const_cast<unsigned char *>(buf), len, off, true);
-}
-
 int bsk_run_file(bsk_ctx *ctx, const char *path, uint64_t off, uint64_t len, int64_t partition_id, const char *out_path,
                  uint64_t out_off, uint64_t *out_bytes, uint64_t *n_records, uint64_t *n_elem) {
   if (!ctx || !path) return BSK_ERR_ARG;
@@ -245,44 +179,16 @@ int bsk_run_file(bsk_ctx *ctx, const char *path, uint64_t off, uint64_t len, int
   const uint64_t fsz = (uint64_t)sb.st_size;
   if (off > fsz) off = fsz;
   if (len == 0 || off + len > fsz) len = fsz - off;
-  int rc = BSK_OK;
-  bsk_out out;
-  memset(&out, 0, sizeof out);
-  bool fd_open = true;
-  const bool dbg = getenv("BSK_DEBUG") != nullptr;
-  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t0 = now();
-  double t1 = t0, t2 = t0, t3 = t0;
-  try {
-    unsigned char *buf = ctx->eng->file_arena(len);  // pinned: the H2D copies of the pipeline are true DMA
-    t1 = now();
-    const bool read_ok = par_io(fd, buf, len, off, false);
-    close(fd);
-    fd_open = false;
-    if (!read_ok) { ctx->eng->err = std::string("short read on ") + path; return BSK_ERR_DATA; }
-    t2 = now();
-    rc = ctx->eng->run_buffer(buf, len, partition_id, &out);
-    t3 = now();
-  } catch (const std::exception &e) {
-    if (fd_open) close(fd);
-    ctx->eng->err = e.what();
-    return BSK_ERR_CUDA;
-  }
-  if (rc != BSK_OK) return rc;
+  int g = -1;
   if (out_path) {
-    const int g = open(out_path, O_RDWR | O_CREAT, 0644);
-    if (g < 0) { ctx->eng->err = std::string("cannot open ") + out_path; return BSK_ERR_ARG; }
-    const bool ok = par_write(g, (const unsigned char *)out.data, out.n, out_off);
-    close(g);
-    if (!ok) { ctx->eng->err = std::string("short write on ") + out_path; return BSK_ERR_DATA; }
+    g = open(out_path, O_RDWR | O_CREAT, 0644);
+    if (g < 0) { close(fd); ctx->eng->err = std::string("cannot open ") + out_path; return BSK_ERR_ARG; }
   }
-  if (dbg)
-    fprintf(stderr, "[bsk_run_file] arena %.3f s, read %.3f s, run_buffer %.3f s, write %.3f s (%llu -> %llu bytes)\n", t1 - t0,
-            t2 - t1, t3 - t2, now() - t3, (unsigned long long)len, (unsigned long long)out.n);
-  if (out_bytes) *out_bytes = out.n;
-  if (n_records) *n_records = out.n_records;
-  if (n_elem) *n_elem = out.n_elem;
-  return BSK_OK;
+  struct Closer {
+    int a, b;
+    ~Closer() { close(a); if (b >= 0) close(b); }
+  } closer{fd, g};
+  BSK_GUARD(ctx, return ctx->eng->run_stream(fd, off, len, partition_id, g, out_off, out_bytes, n_records, n_elem);)
 }
 
 void *bsk_stream(bsk_ctx *ctx) { return ctx ? (void *)ctx->eng->stream : nullptr; }

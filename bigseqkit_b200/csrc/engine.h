@@ -35,8 +35,8 @@ class Engine {
   int run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out);
   int reset();
   int stage_device(const u8 *in, size_t n, void **d_ptr);  // host partition -> the ctx's own device buffer
-  // pinned staging buffer of bsk_run_file (kept across calls)
-  u8 *file_arena(size_t n) { h_file_.reserve(n + 64); return h_file_.as<u8>(); }
+  // file range -> operator -> file through a bounded ring of pinned slots (run_file.cu); out_fd < 0: nothing is written
+  int run_stream(int fd, u64 off, u64 len, int64_t pid, int out_fd, u64 out_off, u64 *out_bytes, u64 *n_records, u64 *n_elem);
 
   // stats
   int stats_result(bsk_stats *out);
@@ -106,7 +106,9 @@ class Engine {
   DevBuf b_tmp_, b_keep_, b_out_len_, b_out_off_, b_out_, b_elem_, b_id_, b_gap_seq_, b_gap_qual_, b_newlen_;
   DevBuf b_tables_, b_lens_sorted_, b_rle_u_, b_rle_c_;
   DevBuf b_op1_, b_op2_, b_op3_, b_op4_, b_op5_, b_op6_, b_op7_, b_op8_;
-  PinnedBuf h_out_, h_elem_, h_small_, h_file_;
+  PinnedBuf h_out_, h_elem_, h_small_;
+  static const int kStreamSlots = 3;
+  PinnedBuf s_in_slot_[kStreamSlots], s_out_slot_[kStreamSlots];  // pinned block slots of run_stream (kept across calls)
   // bsk_run_buffer pipeline: second input / output buffer sets, copy streams, hand-over events
   DevBuf b_in2_, b_out2_, b_elem2_;
   cudaStream_t s_in_ = nullptr, s_out_ = nullptr;
@@ -191,6 +193,9 @@ class Engine {
   int op_grep(BlockOut &bo);
   int op_subseq(BlockOut &bo);
   int op_fq2fa(BlockOut &bo);
+  int op_duplicate(BlockOut &bo);
+  int op_range(BlockOut &bo);
+  u64 range_seen_ = 0;  // records of the partition in front of the running block (RangePrepare index)
   int emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, BlockOut &bo);
   void finalize_stats(bsk_stats *s);
 };

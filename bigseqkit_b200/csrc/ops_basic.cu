@@ -195,6 +195,98 @@ int Engine::op_fq2fa(BlockOut &bo) {
   return emit_records(cfg, nullptr, nullptr, bo);
 }
 
+// ------------------------------------------------------------------ Duplicate, Range (Head)
+// Operators on the RAW elements: record text as it stands minus one trailing '\n' (ReadFixer, bigseqkit-lib/helper.go:51),
+// written back with FileStore's '\n' -- i.e. the bytes of the record, plus a '\n' behind a last record that has none.
+//   Duplicate.Call      bigseqkit-lib/duplicate.go:24-30   every element `times` times
+//   RangePrepare.Call   bigseqkit-lib/range.go:26-31       kept iff start <= index < end (index: MapWithIndex, global)
+//   RangeFilter.Call    bigseqkit-lib/range.go:42-44 ; Head = Range "1:N" (bigseqkit/head.go:33-44)
+__global__ void k_dup_copy(const u8 *__restrict__ in, u32 n, const u32 *__restrict__ head_off, u32 n_rec, u32 times, int add_nl,
+                           u8 *__restrict__ out, u64 *__restrict__ elem_off) {
+  const u32 r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+  if (r >= n_rec) return;
+  const u32 s = head_off[r] - 1u, e = r + 1 < n_rec ? head_off[r + 1] - 1u : n;
+  const u32 len = e - s;
+  const u64 elen = (u64)len + ((r + 1 == n_rec && add_nl) ? 1u : 0u);
+  const u64 base = (u64)times * s;  // every record in front of this one ends with its own '\n'
+  for (u32 c = 0; c < times; c++) {
+    u8 *dst = out + base + c * elen;
+    for (u32 i = lane; i < len; i += 32) dst[i] = in[s + i];
+    if (lane == 0) {
+      if (elen > len) dst[len] = '\n';
+      if (elem_off) elem_off[(u64)r * times + c] = base + c * elen;
+    }
+  }
+}
+__global__ void k_range_elems(const u32 *__restrict__ head_off, u32 a, u32 b, u32 s_a, u64 total, u64 *__restrict__ elem_off) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > b - a) return;
+  elem_off[i] = i == b - a ? total : (u64)(head_off[a + i] - 1u - s_a);
+}
+
+int Engine::op_duplicate(BlockOut &bo) {
+  // (no check_errors(): the reference does not parse the records here, whatever they hold is passed on)
+  if (!n_rec_ || o_.Times == 0) return BSK_OK;
+  if (o_.Times > 0xffffffffll) { err = "duplicate: times is too large"; return BSK_ERR_ARG; }
+  u8 *hs = h_small_.as<u8>();
+  BSK_CUDA(cudaMemcpyAsync(hs, in_ + n_ - 1, 1, cudaMemcpyDeviceToHost, stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  const int add_nl = hs[0] != '\n';
+  const u64 total = (u64)o_.Times * ((u64)n_ + (add_nl ? 1u : 0u));
+  const u64 n_el = (u64)n_rec_ * (u64)o_.Times;
+  u8 *out = b_out_.get<u8>((size_t)total + 64);
+  u64 *elem = want_elem_off ? b_elem_.get<u64>((size_t)n_el + 1) : nullptr;
+  main_begin();
+  BSK_LAUNCH_FLAT(k_dup_copy, (u32)(((u64)n_rec_ * 32 + 255) / 256), 256, 0, stream, in_, n_, ra_.head_off, n_rec_, (u32)o_.Times,
+                  add_nl, out, elem);
+  main_end();
+  launches_++;
+  if (elem) {
+    memcpy(hs, &total, 8);
+    BSK_CUDA(cudaMemcpyAsync(elem + n_el, hs, 8, cudaMemcpyHostToDevice, stream));
+  }
+  bo.d_data = out;
+  bo.n = total;
+  bo.d_elem_off = elem;
+  bo.n_elem = n_el;
+  return BSK_OK;
+}
+
+int Engine::op_range(BlockOut &bo) {
+  if (first_block_) range_seen_ = 0;
+  const int64_t idx0 = o_.IndexBase + (int64_t)range_seen_;  // global index of this block's first record
+  range_seen_ += n_rec_;
+  int64_t a = o_.RangeStart - idx0, b = o_.RangeEnd > idx0 + (int64_t)n_rec_ ? (int64_t)n_rec_ : o_.RangeEnd - idx0;
+  if (a < 0) a = 0;
+  if (b > (int64_t)n_rec_) b = n_rec_;
+  if (b <= a) return BSK_OK;
+  u32 *hs = h_small_.as<u32>();
+  BSK_CUDA(cudaMemcpyAsync(hs, ra_.head_off + a, 4, cudaMemcpyDeviceToHost, stream));
+  if (b < (int64_t)n_rec_) BSK_CUDA(cudaMemcpyAsync(hs + 1, ra_.head_off + b, 4, cudaMemcpyDeviceToHost, stream));
+  BSK_CUDA(cudaMemcpyAsync(hs + 2, in_ + n_ - 1, 1, cudaMemcpyDeviceToHost, stream));
+  BSK_CUDA(cudaStreamSynchronize(stream));
+  const u32 s_a = hs[0] - 1u, s_b = b < (int64_t)n_rec_ ? hs[1] - 1u : n_;
+  const bool add_nl = b == (int64_t)n_rec_ && *reinterpret_cast<const u8 *>(hs + 2) != '\n';
+  const u64 total = (u64)(s_b - s_a) + (add_nl ? 1u : 0u);
+  u8 *out = b_out_.get<u8>((size_t)total + 64);
+  main_begin();
+  BSK_CUDA(cudaMemcpyAsync(out, in_ + s_a, s_b - s_a, cudaMemcpyDeviceToDevice, stream));
+  if (add_nl) BSK_CUDA(cudaMemsetAsync(out + total - 1, '\n', 1, stream));
+  main_end();
+  const u32 n_el = (u32)(b - a);
+  u64 *elem = nullptr;
+  if (want_elem_off) {
+    elem = b_elem_.get<u64>((size_t)n_el + 1);
+    BSK_LAUNCH_FLAT(k_range_elems, (n_el + 1 + 255) / 256, 256, 0, stream, ra_.head_off, (u32)a, (u32)b, s_a, total, elem);
+    launches_++;
+  }
+  bo.d_data = out;
+  bo.n = total;
+  bo.d_elem_off = elem;
+  bo.n_elem = n_el;
+  return BSK_OK;
+}
+
 // ------------------------------------------------------------------ Stats
 // bigseqkit-lib/stats.go:48-117 (per partition) ; totals are kept with sum semantics
 int Engine::op_stats(BlockOut &bo) {

@@ -653,6 +653,7 @@ int Engine::op_locate_tile(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
     }
     if (n_hits <= hit_cap_) break;
     hit_cap_ = n_hits + n_hits / 4 + 1024;  // the hit buffer was too small: grow and match again
+    main_timed_ = false;
     timings.main_launches--;
   }
   // record table: headers in input order, newline prefix over the tiles

@@ -90,6 +90,8 @@ Op op_from_name(const char *n) {
   if (!strcmp(n, "Grep") || !strcmp(n, "grep")) return OP_GREP;
   if (!strcmp(n, "SubseqTransform") || !strcmp(n, "subseq")) return OP_SUBSEQ;
   if (!strcmp(n, "Fq2Fa") || !strcmp(n, "fq2fa")) return OP_FQ2FA;
+  if (!strcmp(n, "Duplicate") || !strcmp(n, "duplicate")) return OP_DUPLICATE;
+  if (!strcmp(n, "RangePrepare") || !strcmp(n, "Range") || !strcmp(n, "range") || !strcmp(n, "Head") || !strcmp(n, "head")) return OP_RANGE;
   return OP_INVALID;
 }
 
@@ -104,6 +106,10 @@ void jbool(const JValue &o, const char *k, bool &dst) {
 void jint(const JValue &o, const char *k, int &dst) {
   const JValue *v = o.get(k);
   if (v && v->kind == JValue::Num) dst = (int)v->num;
+}
+void ji64(const JValue &o, const char *k, int64_t &dst) {
+  const JValue *v = o.get(k);
+  if (v && v->kind == JValue::Num) dst = (int64_t)v->num;
 }
 void jdbl(const JValue &o, const char *k, double &dst) {
   const JValue *v = o.get(k);
@@ -225,6 +231,16 @@ bool parse_and_validate(Op op, const char *json, Opts &o, std::string &err, int 
   jbool(root, "InvertMatch", o.InvertMatch); jbool(root, "Count", o.Count); jbool(root, "DeleteMatched", o.DeleteMatched);
   jint(root, "MaxMismatch", o.MaxMismatch);
   jstr(root, "Region", o.Region);
+  // Duplicate: vars "times" (bigseqkit-lib/duplicate.go:20); RangePrepare: vars "start" / "end" (range.go:20-24);
+  // Head: N (bigseqkit/head.go:33-44 = Range "1:N", i.e. start 0, end N); IndexBase = global index of the partition's
+  // first record (what MapWithIndex supplies)
+  ji64(root, "Times", o.Times); ji64(root, "times", o.Times);
+  ji64(root, "Start", o.RangeStart); ji64(root, "start", o.RangeStart);
+  ji64(root, "End", o.RangeEnd); ji64(root, "end", o.RangeEnd);
+  ji64(root, "IndexBase", o.IndexBase);
+  if (const JValue *nv = root.get("N")) {
+    if (nv->kind == JValue::Num) { o.RangeStart = 0; o.RangeEnd = (int64_t)nv->num; }
+  }
   if (op == OP_SUBSEQ) { jstr(root, "Gtf", o.SubseqGtf); jstr(root, "Bed", o.SubseqBed); }
   else { jbool(root, "Gtf", o.Gtf); jbool(root, "Bed", o.Bed); }
   if (o.IDNCBI) o.IDRegexp = "\\|([^\\|]+)\\| ";  // bigseqkit/helper.go:97-100
@@ -374,6 +390,11 @@ bool parse_and_validate(Op op, const char *json, Opts &o, std::string &err, int 
       if (!parse_region(o.Region, "subseq", o.region_start, o.region_end, err)) return false;
       break;
     case OP_FQ2FA:  // bigseqkit/fq2fa.go:11-18: KitConfig only
+      break;
+    case OP_DUPLICATE:
+      if (o.Times < 0) { err = "times must be >= 0"; return false; }  // make([]string, times) panics below zero
+      break;
+    case OP_RANGE:
       break;
     default:
       err = "unknown operator";

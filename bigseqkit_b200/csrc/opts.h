@@ -7,6 +7,8 @@
 //   LocateOptions        bigseqkit/locate.go:9-45
 //   GrepOptions          bigseqkit/grep.go:13-49
 //   SubseqOptions        bigseqkit/subseq.go:9-35
+//   DuplicateOptions     bigseqkit/duplicate.go (Times) ; RangePrepare vars start / end (bigseqkit-lib/range.go:20-24) ;
+//   HeadOptions          bigseqkit/head.go:12-22 (N)
 // The JSON field names are the Go field names (encoding/json of the struct).
 #pragma once
 #include <cstdint>
@@ -15,7 +17,7 @@
 
 namespace bsk {
 
-enum Op { OP_SEQ, OP_STATS, OP_RMDUP, OP_RMDUP_PREPARE, OP_TRANSLATE, OP_LOCATE, OP_GREP, OP_SUBSEQ, OP_FQ2FA, OP_INVALID };
+enum Op { OP_SEQ, OP_STATS, OP_RMDUP, OP_RMDUP_PREPARE, OP_TRANSLATE, OP_LOCATE, OP_GREP, OP_SUBSEQ, OP_FQ2FA, OP_DUPLICATE, OP_RANGE, OP_INVALID };
 
 // alphabets of shenwei356/bio v0.7.0 seq/alphabet.go as used by the reference
 enum Alphabet { AB_NIL = 0, AB_DNA, AB_DNARED, AB_RNA, AB_RNARED, AB_PROTEIN, AB_UNLIMIT, AB_COUNT };
@@ -63,6 +65,8 @@ struct Opts {
   // SubseqOptions / Grep region
   std::string Region;
   std::string SubseqGtf, SubseqBed;
+  // Duplicate (times), RangePrepare (start, end: 0-based, half-open, as the operator receives them), Head (N)
+  int64_t Times = 1, RangeStart = 0, RangeEnd = INT64_MAX, IndexBase = 0;
 
   // derived in validate()
   int alphabet = AB_NIL;       // from SeqType (AB_NIL = auto)

@@ -1197,6 +1197,41 @@ int orc_fq2fa(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out) {
   return rc < 0 ? -1 : 0;
 }
 
+/* ------------------------------------------------------- duplicate / range / head
+ * Operators on the RAW elements (record text minus one trailing '\n'); FileStore writes element + '\n'.
+ *   Duplicate.Call      lib/duplicate.go:24-30   every element `times` times
+ *   RangePrepare.Call   lib/range.go:26-31       element kept iff start <= index < end, index = global 0-based position
+ *   RangeFilter.Call    lib/range.go:42-44       (MapWithIndex; drops the "" placeholders)
+ *   Head                bigseqkit/head.go:33-44   = Range("1:N"), i.e. start 0, end N
+ * The snapshot's driver rejects every start <= end (bigseqkit/range.go:85), so range / head cannot run there; the
+ * library operators are restated with the semantics their code states. */
+static void raw_elem(sink_t *sink, const uint8_t *d, uint64_t a, uint64_t b) {
+  if (b > a && d[b - 1] == '\n') b--;
+  sink_elem(sink, d + a, b - a);
+}
+int orc_duplicate(const uint8_t *data, size_t n, int64_t times, orc_out *out) {
+  memset(out, 0, sizeof *out);
+  uint64_t *st; size_t cnt = orc_frame(data, n, &st);
+  sink_t sink; memset(&sink, 0, sizeof sink);
+  for (size_t r = 0; r < cnt; r++)
+    for (int64_t t = 0; t < times; t++) raw_elem(&sink, data, st[r], st[r + 1]);
+  sink_to_out(&sink, out);
+  free(st);
+  return 0;
+}
+int orc_range(const uint8_t *data, size_t n, int64_t start, int64_t end, int64_t index_base, orc_out *out) {
+  memset(out, 0, sizeof *out);
+  uint64_t *st; size_t cnt = orc_frame(data, n, &st);
+  sink_t sink; memset(&sink, 0, sizeof sink);
+  for (size_t r = 0; r < cnt; r++) {
+    const int64_t idx = index_base + (int64_t)r;
+    if (start <= idx && idx < end) raw_elem(&sink, data, st[r], st[r + 1]);
+  }
+  sink_to_out(&sink, out);
+  free(st);
+  return 0;
+}
+
 /* ------------------------------------------------- multi-threaded CPU baseline
  * Record-aligned byte-range shards, one thread each (the restatement of
  * "IgnisHPC partitions x executor threads").  rmdup: parallel Prepare, keys

@@ -101,6 +101,9 @@ int orc_grep(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
 int orc_subseq(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
 /* Fq2Fa.Call (lib/fq2fa.go:36-61) */
 int orc_fq2fa(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out);
+/* raw-element operators (lib/duplicate.go:24-30, lib/range.go:26-44, bigseqkit/head.go:33-44) */
+int orc_duplicate(const uint8_t *data, size_t n, int64_t times, orc_out *out);
+int orc_range(const uint8_t *data, size_t n, int64_t start, int64_t end, int64_t index_base, orc_out *out);
 
 /* leaf helpers exposed for known-answer tests */
 size_t orc_subseq_range(size_t len, int start, int end, size_t *s0); /* returns length, *s0 = 0-based start */

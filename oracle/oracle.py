@@ -215,6 +215,23 @@ def fq2fa(data, opts=None):
     return _run("orc_fq2fa", data, opts)
 
 
+def duplicate(data, times):
+    out = _Out()
+    rc = lib().orc_duplicate(data, len(data), C.c_int64(times), C.byref(out))
+    return _take(out, rc)
+
+
+def range_(data, start, end, index_base=0):
+    """RangePrepare + RangeFilter with the 0-based half-open bounds the library operator receives"""
+    out = _Out()
+    rc = lib().orc_range(data, len(data), C.c_int64(start), C.c_int64(end), C.c_int64(index_base), C.byref(out))
+    return _take(out, rc)
+
+
+def head(data, n):
+    return range_(data, 0, n)
+
+
 def rmdup(data, opts=None):
     keep = []
     o = _mk_opts(opts, keep)

@@ -42,3 +42,40 @@ def test_shard_bounds_fasta_and_tricky_quality_lines(lib, tmp_path):
     q = tmp_path / "t.fq"
     q.write_bytes(tricky)
     assert all(x % 15 == 0 for x in api.shard_bounds(str(q), 9, lib=lib))
+
+
+def test_streamed_range_many_blocks(lib, tmp_path, monkeypatch):
+    # bsk_run_file streams the range through a ring of pinned slots: many small blocks, state carried from block to block,
+    # one record longer than a block (the slot grows), output written block by block at its running offset
+    monkeypatch.setenv("BSK_BLOCK_BYTES", "8192")
+    fq = synth.fastq_reads(150 << 10, seed=97, dup_frac=0.3).tobytes()
+    fa = (synth.fasta_cds(60 << 10, seed=98).tobytes() + b">long\n" + b"ACGTTGCAAC" * 3000 + b"\n"
+          + synth.fasta_cds(20 << 10, seed=99).tobytes())
+    cases = [
+        ("SeqTransform", {"Reverse": True, "Complement": True}, fq, oracle.seq),
+        ("SeqTransform", {"MinLen": 120}, fq, oracle.seq),
+        ("RmDup", {"BySeq": True}, fq, lambda d, o: oracle.rmdup(d, o)[:2]),
+        ("Translate", {"Frame": ["6"]}, fa, oracle.translate),
+        ("SeqTransform", {"Complement": True}, fa, oracle.seq),
+        ("Fq2Fa", {}, fq, oracle.fq2fa),
+    ]
+    for k, (opn, opts, data, ref) in enumerate(cases):
+        src = tmp_path / ("in%d" % k)
+        src.write_bytes(data)
+        out = tmp_path / ("out%d" % k)
+        exp = ref(data, opts)[0]
+        with Operator(opn, opts, lib=lib) as op:
+            ob, nr, ne = op.call_file(str(src), 0, 0, str(out), 0)
+        assert ob == len(exp), (opn, opts)
+        assert out.read_bytes() == exp, (opn, opts)
+    # stats: no output, the histogram accumulates over the blocks
+    src = tmp_path / "s.fq"
+    src.write_bytes(fq)
+    with Operator("Stats", {"Tabular": True, "All": True}, lib=lib) as op:
+        ob, nr, ne = op.call_file(str(src))
+        assert ob == 0 and op.stats_render() == oracle.stats(fq, {"Tabular": True, "All": True})[1]
+    # empty file
+    e = tmp_path / "empty.fq"
+    e.write_bytes(b"")
+    with Operator("SeqTransform", {}, lib=lib) as op:
+        assert op.call_file(str(e), 0, 0, str(tmp_path / "eo"), 0)[0] == 0
