@@ -44,7 +44,7 @@ class _Timings(C.Structure):
 # every symbol include/bsk.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "bsk_version", "bsk_device_count", "bsk_create", "bsk_create_error", "bsk_destroy", "bsk_last_error",
-    "bsk_set_elem_offsets", "bsk_reset", "bsk_run_buffer", "bsk_run_device", "bsk_stream", "bsk_get_timings",
+    "bsk_set_elem_offsets", "bsk_set_union", "bsk_reset", "bsk_run_buffer", "bsk_run_device", "bsk_stream", "bsk_get_timings",
     "bsk_stats_result", "bsk_stats_merge", "bsk_stats_add", "bsk_stats_dense_device", "bsk_stats_render",
     "bsk_shard_bounds", "bsk_run_file", "bsk_rmdup_keys", "bsk_rmdup_removed", "bsk_rmdup_dup_seqs", "bsk_rmdup_dup_num", "bsk_rmdup_prepare_device", "bsk_rmdup_resolve_device", "bsk_grep_count",
     "bsk_comm_unique_id", "bsk_comm_error", "bsk_comm_init", "bsk_comm_rank", "bsk_comm_free", "bsk_output_offsets",
@@ -69,6 +69,7 @@ class Library:
         L.bsk_last_error.argtypes = [vp]
         L.bsk_last_error.restype = C.c_char_p
         L.bsk_set_elem_offsets.argtypes = [vp, C.c_int]
+        L.bsk_set_union.argtypes = [vp, C.c_int]
         L.bsk_reset.argtypes = [vp]
         L.bsk_run_buffer.argtypes = [vp, vp, sz, i64, C.POINTER(_Out)]
         L.bsk_run_device.argtypes = [vp, vp, sz, i64, C.POINTER(_Out)]
@@ -187,6 +188,10 @@ class Operator:
 
     def set_elem_offsets(self, want):
         self._check(self.lib.cdll.bsk_set_elem_offsets(self.h, 1 if want else 0))
+
+    def set_union(self, on=True):
+        """the partitions of the following calls are one dataframe (rmdup dedups across them, range keeps counting)"""
+        self._check(self.lib.cdll.bsk_set_union(self.h, 1 if on else 0))
 
     def reset(self):
         self._check(self.lib.cdll.bsk_reset(self.h))

@@ -1,16 +1,26 @@
-"""`bigseqkit <cmd> [flags] files...` -- the reference CLI surface (bigseqkit-cli/*.go, cobra) for the seven
-accelerated commands, on top of libbsk.so.  Flag names, shorthands and defaults follow bigseqkit-cli/seq.go:54-73,
-stats.go:61-65, rmdup.go:45-51, locate.go:61-75, grep.go:81-96, subseq.go:56-67, translate.go:86-94 and the
-persistent flags of bigseqkit-cli/helper.go:161-173.  Input type is sniffed like helper.go:47-85; outputs go to
-`-o` (default `<first input>-out`, helper.go:108-121) as ONE file (the reference's --merge layout); `stats` prints
-its table to stdout (bigseqkit-cli/stats.go:10-28).
+"""`bigseqkit <cmd> [flags] files...` -- the reference CLI surface (bigseqkit-cli/*.go, cobra) for the accelerated
+commands, on top of libbsk.so.  Flag names, shorthands and defaults follow bigseqkit-cli/seq.go:54-73,
+stats.go:61-65, rmdup.go:45-51, locate.go:61-75, grep.go:81-96, subseq.go:56-67, translate.go:86-94, duplicate.go,
+range.go, head.go and the persistent flags of bigseqkit-cli/helper.go:161-173.  Input type is sniffed like
+helper.go:47-85; `stats` prints its table to stdout (bigseqkit-cli/stats.go:10-28).
+
+Partitions and devices.  Every input file is cut into `--partitions` record-aligned ranges (bsk_shard_bounds; default
+one per file) and the ranges are handed round-robin to the CUDA devices of `--devices` (one ctx and one host thread
+each); every range streams file -> HBM -> file through bsk_run_file.  Outputs go to `-o` (default `<first input>-out`,
+helper.go:108-121): one file in partition order with --merge or when there is a single partition (StoreFASTX), else a
+directory of `part<k>` files (StoreFASTXN).  `rmdup` and `range` / `head` see all partitions as ONE dataframe, in input
+order (the reference Unions the inputs, helper.go:131-138): they run on the first device with bsk_set_union.
 
     python -m bigseqkit_b200.cli seq -r -p reads.fq -o out.fq
+    python -m bigseqkit_b200.cli translate -f 6 --partitions 8 --devices 0,1,2,3 --merge cds.fa -o prot.fa
 """
 import argparse
+import os
+import shutil
 import sys
+import threading
 
-from .api import BskError, Operator
+from .api import BskError, Operator, shard_bounds
 
 
 def _persistent(p):
@@ -26,6 +36,7 @@ def _persistent(p):
     p.add_argument("--partitions", type=int, default=0)
     p.add_argument("--order", action="store_true")
     p.add_argument("--device", type=int, default=0, help="CUDA device (not in the reference: executors pick one each)")
+    p.add_argument("--devices", default="", help="comma list of CUDA devices the partitions are spread over (overrides --device)")
     p.add_argument("files", nargs="*")
 
 
@@ -109,6 +120,18 @@ def build_parser():
     p = sub.add_parser("fq2fa", help="convert FASTQ to FASTA")  # bigseqkit-cli/fq2fa.go:27-28
     _persistent(p)
 
+    p = sub.add_parser("duplicate", help="duplicate sequences N times")  # bigseqkit-cli/duplicate.go
+    p.add_argument("-n", "--times", type=int, default=1)
+    _persistent(p)
+
+    p = sub.add_parser("range", help="print FASTA/Q records in a range (start:end)")  # bigseqkit-cli/range.go
+    p.add_argument("-r", "--range", default="")
+    _persistent(p)
+
+    p = sub.add_parser("head", help="print first N FASTA/Q records")  # bigseqkit-cli/head.go
+    p.add_argument("-n", "--number", type=int, default=10)
+    _persistent(p)
+
     p = sub.add_parser("translate", help="translate DNA/RNA to protein sequence (supporting ambiguous bases)")
     p.add_argument("-T", "--transl-table", type=int, default=1)
     p.add_argument("-f", "--frame", action="append", default=[])
@@ -176,6 +199,12 @@ def options(a):
                                    "Bed": a.bed, "GtfTag": a.gtf_tag}
     if c == "fq2fa":
         return "Fq2Fa", {"Config": cfg}
+    if c == "duplicate":
+        return "Duplicate", {"Config": cfg, "Times": a.times}
+    if c == "head":  # bigseqkit/head.go:33-44: Range "1:N"
+        return "Range", {"Config": cfg, "Start": 0, "End": a.number}
+    if c == "range":
+        return "Range", dict(_parse_range(a.range), Config=cfg)
     if c == "translate":
         return "Translate", {"Config": cfg, "TranslTable": a.transl_table, "Frame": _split_csv(a.frame) or ["1"],
                              "Trim": a.trim, "Clean": a.clean, "AllowUnknownCodon": a.allow_unknown_codon,
@@ -183,6 +212,22 @@ def options(a):
                              "ListTranslTableWithAmbCodons": a.list_transl_table_with_amb_codons,
                              "AppendFrame": a.append_frame}
     raise SystemExit("unknown command " + c)
+
+
+def _parse_range(r):
+    """-r start:end, 1-based and inclusive like seqkit range (bigseqkit/range.go:46-76).  The snapshot's driver then
+    rejects every start <= end (range.go:85), so the command cannot run there; the intended reading is used here:
+    records start .. end.  Negative bounds (counted from the end) need the record count and are not supported."""
+    if r == "":
+        raise SystemExit("flag -r (--range) needed")
+    parts = r.split(":")
+    start = int(parts[0])
+    end = int(parts[1]) if len(parts) > 1 else -1
+    if start == 0 or end == 0:
+        raise SystemExit("either start and end should not be 0")
+    if start < 0 or end < -1:
+        raise SystemExit("negative range bounds are not supported")
+    return {"Start": start - 1, "End": (1 << 62) if end == -1 else end}
 
 
 def input_files(a):
@@ -194,39 +239,117 @@ def input_files(a):
     return files
 
 
+def _devices(a):
+    if a.devices:
+        return [int(x) for x in a.devices.split(",") if x != ""]
+    return [a.device]
+
+
+def _plan(files, partitions):
+    """[(file, offset, length)] in input order: every file cut into `partitions` record-aligned ranges"""
+    plan = []
+    for f in files:
+        if partitions and partitions > 1:
+            b = shard_bounds(f, partitions)
+            plan += [(f, b[i], b[i + 1] - b[i]) for i in range(partitions) if b[i + 1] > b[i] or i == 0]
+        else:
+            plan.append((f, 0, 0))
+    return plan
+
+
 def main(argv=None):
     a = build_parser().parse_args(argv)
     op_name, opts = options(a)
     files = input_files(a)
+    devices = _devices(a)
     try:
         if a.cmd == "stats":  # one header + one row per input, file label input<i>, format label N/A (cli/stats.go:10-25)
             rows = []
             for i, f in enumerate(files):
-                with Operator("Stats", opts, device=a.device) as op:
-                    op.call_file(f)  # bsk_run_file: pinned staging, pipelined H2D
-                    rows.append(op.stats_render("input%d" % i, "N/A"))
+                parts = _plan([f], a.partitions)
+                ops = [Operator("Stats", opts, device=d) for d in devices[:len(parts)]]
+                try:
+                    def work(k, op):
+                        for j in range(k, len(parts), len(ops)):
+                            op.call_file(parts[j][0], parts[j][1], parts[j][2], partition_id=j)
+                    _run_threads(work, ops)
+                    for other in ops[1:]:  # StatsReduce: sum semantics (bigseqkit-lib/stats.go:119-137)
+                        ops[0].stats_merge(other)
+                    rows.append(ops[0].stats_render("input%d" % i, "N/A"))
+                finally:
+                    for op in ops:
+                        op.close()
             out = rows[0] + "".join(r.split("\n", 1)[1] for r in rows[1:]) if a.tabular else "".join(rows)
             sys.stdout.write(out)
             return 0
         out_path = a.out_file or (files[0] + "-out" if len(files) == 1 else None)
         if out_path is None:
             raise SystemExit("out file -o required")
-        open(out_path, "wb").close()
-        off = 0
-        with Operator(op_name, opts, device=a.device) as op:
-            op.set_elem_offsets(False)  # the merged file needs no element table
-            for i, f in enumerate(files):  # every input file is one partition; outputs are appended in order
-                off += op.call_file(f, 0, 0, out_path, off, partition_id=i)[0]
-                if a.cmd == "rmdup":  # written per input like After does per executor (bigseqkit-lib/rmdup.go:245-275)
-                    mode = "wb" if i == 0 else "ab"
+        plan = _plan(files, a.partitions)
+        one_dataframe = a.cmd in ("rmdup", "range", "head")
+        single = len(plan) == 1 or one_dataframe
+        if single:  # one ctx, partitions in order, output appended as it is produced
+            open(out_path, "wb").close()
+            off = 0
+            with Operator(op_name, opts, device=devices[0]) as op:
+                op.set_elem_offsets(False)  # the merged file needs no element table
+                op.set_union(one_dataframe)
+                for i, (f, o, n) in enumerate(plan):
+                    off += op.call_file(f, o, n, out_path, off, partition_id=i)[0]
+                if a.cmd == "rmdup":  # bigseqkit-lib/rmdup.go:245-275
                     if a.dup_seqs_file:
-                        open(a.dup_seqs_file, mode).write(op.rmdup_dup_seqs())
+                        open(a.dup_seqs_file, "wb").write(op.rmdup_dup_seqs())
                     if a.dup_num_file:
-                        open(a.dup_num_file, mode).write(op.rmdup_dup_num())
+                        open(a.dup_num_file, "wb").write(op.rmdup_dup_num())
+            return 0
+        # several independent partitions: one part file each, spread over the devices
+        part_dir = out_path + ".parts" if a.merge else out_path
+        if os.path.isdir(part_dir):
+            shutil.rmtree(part_dir)
+        elif os.path.exists(part_dir):
+            os.remove(part_dir)
+        os.makedirs(part_dir)
+        names = [os.path.join(part_dir, "part%05d" % k) for k in range(len(plan))]
+        ops = [Operator(op_name, opts, device=d) for d in devices[:len(plan)]]
+        try:
+            def work(k, op):
+                op.set_elem_offsets(False)
+                for j in range(k, len(plan), len(ops)):
+                    open(names[j], "wb").close()
+                    op.call_file(plan[j][0], plan[j][1], plan[j][2], names[j], 0, partition_id=j)
+            _run_threads(work, ops)
+        finally:
+            for op in ops:
+                op.close()
+        if a.merge:
+            with open(out_path, "wb") as dst:
+                for nm in names:
+                    with open(nm, "rb") as src:
+                        shutil.copyfileobj(src, dst, 16 << 20)
+            shutil.rmtree(part_dir)
     except BskError as e:
         sys.stderr.write("bigseqkit: %s\n" % e)
         return 1
     return 0
+
+
+def _run_threads(work, ops):
+    """work(k, ops[k]) on one host thread per ctx (ctypes releases the GIL inside libbsk); the first error is re-raised"""
+    errs = []
+
+    def guarded(k, op):
+        try:
+            work(k, op)
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=guarded, args=(k, op)) for k, op in enumerate(ops)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
 
 
 if __name__ == "__main__":

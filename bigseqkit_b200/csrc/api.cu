@@ -101,6 +101,12 @@ int bsk_set_elem_offsets(bsk_ctx *ctx, int want) {
   return BSK_OK;
 }
 
+int bsk_set_union(bsk_ctx *ctx, int on) {
+  if (!ctx) return BSK_ERR_ARG;
+  ctx->eng->set_union(on != 0);
+  return BSK_OK;
+}
+
 int bsk_reset(bsk_ctx *ctx) {
   if (!ctx) return BSK_ERR_ARG;
   BSK_GUARD(ctx, return ctx->eng->reset();)

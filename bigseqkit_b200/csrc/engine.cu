@@ -73,6 +73,7 @@ int Engine::reset() {
   alphabet_known_ = false;
   first_block_ = true;
   any_record_ = false;
+  range_seen_ = 0;
   reset_op_state();
   return BSK_OK;
 }

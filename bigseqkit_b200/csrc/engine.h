@@ -34,6 +34,9 @@ class Engine {
   int run_device(const void *d_in, size_t n, int64_t pid, bsk_out *out);
   int run_buffer(const u8 *in, size_t n, int64_t pid, bsk_out *out);
   int reset();
+  // partitions of one Union (bigseqkit-cli/helper.go:131-138): the rmdup key table / history and the Range index keep
+  // running from call to call until reset()
+  void set_union(bool on) { union_ = on; }
   int stage_device(const u8 *in, size_t n, void **d_ptr);  // host partition -> the ctx's own device buffer
   // file range -> operator -> file through a bounded ring of pinned slots (run_file.cu); out_fd < 0: nothing is written
   int run_stream(int fd, u64 off, u64 len, int64_t pid, int out_fd, u64 out_off, u64 *out_bytes, u64 *n_records, u64 *n_elem);
@@ -195,6 +198,7 @@ class Engine {
   int op_fq2fa(BlockOut &bo);
   int op_duplicate(BlockOut &bo);
   int op_range(BlockOut &bo);
+  bool union_ = false;
   u64 range_seen_ = 0;  // records of the partition in front of the running block (RangePrepare index)
   int emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, BlockOut &bo);
   void finalize_stats(bsk_stats *s);

@@ -253,7 +253,7 @@ int Engine::op_duplicate(BlockOut &bo) {
 }
 
 int Engine::op_range(BlockOut &bo) {
-  if (first_block_) range_seen_ = 0;
+  if (first_block_ && !union_) range_seen_ = 0;
   const int64_t idx0 = o_.IndexBase + (int64_t)range_seen_;  // global index of this block's first record
   range_seen_ += n_rec_;
   int64_t a = o_.RangeStart - idx0, b = o_.RangeEnd > idx0 + (int64_t)n_rec_ ? (int64_t)n_rec_ : o_.RangeEnd - idx0;

@@ -423,7 +423,7 @@ int Engine::rmdup_dup_num(const char **data, size_t *n) {
 int Engine::op_rmdup(BlockOut &bo, bool prepare_only) {
   int rc = check_errors();
   if (rc != BSK_OK) return rc;
-  if (first_block_) {  // a new partition: forget the previous one
+  if (first_block_ && !union_) {  // a new partition: forget the previous one (unless the partitions are one Union)
     if (rm_) rmdup_state_reset(rm_);
     rmdup_removed = 0;
   }
@@ -533,7 +533,7 @@ int Engine::op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only
   set_views_default();
   bo.n_rec = n_rec_;
   if (n_rec_) any_record_ = true;
-  if (first_block_) {  // a new partition: forget the previous one
+  if (first_block_ && !union_) {  // a new partition: forget the previous one (unless the partitions are one Union)
     if (rm_) rmdup_state_reset(rm_);
     rmdup_removed = 0;
   }

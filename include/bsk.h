@@ -109,6 +109,11 @@ void bsk_destroy(bsk_ctx *ctx);
 const char *bsk_last_error(const bsk_ctx *ctx);
 /* want_elem_off != 0: fill bsk_out.elem_off (default on). */
 int bsk_set_elem_offsets(bsk_ctx *ctx, int want_elem_off);
+/* on != 0: the partitions of the following calls are ONE dataframe (bigseqkit-cli/helper.go:131-138 Unions all input
+ * files before the operator runs; bigseqkit/rmdup.go:97 groups keys over all partitions): the rmdup key table and
+ * history and the RangePrepare record index (bigseqkit-lib/range.go:26-31, MapWithIndex) keep running from call to
+ * call, in call order, until bsk_reset.  Default off: every call is a partition of its own. */
+int bsk_set_union(bsk_ctx *ctx, int on);
 /* forget accumulated state (stats totals, rmdup keys) */
 int bsk_reset(bsk_ctx *ctx);
 

@@ -64,3 +64,37 @@ def test_cli_end_to_end(lib, monkeypatch, tmp_path, capsys):
     # a flag error surfaces with the reference's text and a non-zero status
     assert _run_cli(lib, monkeypatch, ["seq", "-l", "-u", str(fa), "-o", str(tmp_path / "o4")]) == 1
     assert "could not give both flags -l (--lower-case) and -u (--upper-case)" in capsys.readouterr().err
+
+
+def test_cli_partitions_union_and_new_commands(lib, monkeypatch, tmp_path, capsys):
+    from bigseqkit_b200 import synth
+    fq = synth.fastq_reads(60 << 10, seed=41, dup_frac=0.3).tobytes()
+    a, b = tmp_path / "a.fq", tmp_path / "b.fq"
+    a.write_bytes(fq)
+    b.write_bytes(fq[: len(fq) // 2 and oracle.frame(fq)[len(oracle.frame(fq)) // 2]])
+    both = a.read_bytes() + b.read_bytes()
+    # rmdup over several inputs dedups the Union of them (bigseqkit-cli/helper.go:131-138, bigseqkit/rmdup.go:97)
+    assert _run_cli(lib, monkeypatch, ["rmdup", "-s", str(a), str(b), "-o", str(tmp_path / "u.fq")]) == 0
+    assert (tmp_path / "u.fq").read_bytes() == oracle.rmdup(both, {"BySeq": True})[0]
+    # ... and over the partitions of one input
+    assert _run_cli(lib, monkeypatch, ["rmdup", "-s", "--partitions", "3", str(a), "-o", str(tmp_path / "u3.fq")]) == 0
+    assert (tmp_path / "u3.fq").read_bytes() == oracle.rmdup(fq, {"BySeq": True})[0]
+    # partitions + --merge: one file in partition order; without --merge: a directory of parts (StoreFASTXN)
+    exp = oracle.seq(fq, {"Reverse": True, "Complement": True})[0]
+    assert _run_cli(lib, monkeypatch, ["seq", "-r", "-p", "--partitions", "4", "--merge", str(a), "-o", str(tmp_path / "m.fq")]) == 0
+    assert (tmp_path / "m.fq").read_bytes() == exp
+    assert _run_cli(lib, monkeypatch, ["seq", "-r", "-p", "--partitions", "4", str(a), "-o", str(tmp_path / "parts")]) == 0
+    names = sorted(os.listdir(tmp_path / "parts"))
+    assert names == ["part%05d" % k for k in range(4)]
+    assert b"".join((tmp_path / "parts" / n).read_bytes() for n in names) == exp
+    # stats over partitions: histograms merged with sum semantics
+    capsys.readouterr()
+    assert _run_cli(lib, monkeypatch, ["stats", "-T", "-a", "--partitions", "3", str(a)]) == 0
+    assert capsys.readouterr().out == oracle.stats(fq, {"Tabular": True, "All": True})[1]
+    # duplicate / head / range
+    assert _run_cli(lib, monkeypatch, ["duplicate", "-n", "3", str(a), "-o", str(tmp_path / "d3")]) == 0
+    assert (tmp_path / "d3").read_bytes() == oracle.duplicate(fq, 3)[0]
+    assert _run_cli(lib, monkeypatch, ["head", "-n", "7", "--partitions", "2", str(a), str(b), "-o", str(tmp_path / "h7")]) == 0
+    assert (tmp_path / "h7").read_bytes() == oracle.head(both, 7)[0]
+    assert _run_cli(lib, monkeypatch, ["range", "-r", "5:9", str(a), "-o", str(tmp_path / "r59")]) == 0
+    assert (tmp_path / "r59").read_bytes() == oracle.range_(fq, 4, 9)[0]

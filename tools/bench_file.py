@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Scope F of SURVEY section 8d: file -> file wall clock of `seq -r -p` through bsk_run_file (read into the pinned
-arena, pipelined H2D / kernel / D2H, write at the output offset), with the file in the page cache (tmpfs when
-available).  One JSON line per I/O thread count; the CPU port (oracle, all threads, in memory) beside it."""
+"""Scope F of SURVEY section 8d: file -> file wall clock of `seq -r -p` through bsk_run_file (reader thread -> pinned
+slots -> H2D / kernels / D2H -> writer thread, all overlapped; host memory bounded by six 64 MiB slots), with the file
+in the page cache (tmpfs when available).  One JSON line per I/O thread count; the CPU port (oracle, all threads, in
+memory) beside it."""
 import argparse
 import json
 import os
