@@ -222,7 +222,6 @@ __global__ void __launch_bounds__(rt::G::NT, rt::G::CTAS) k_rmdup_tile(RmdupTile
         u64 t = XXP5;
         key_fp_tail(gw, 32u * ns, slen, h, t);
         if (act && gl == 0) {
-          if (a.subject != 2) idl = rt_id_len(d + p0 + 1, hl);
           RmdupSlot sl_;
           sl_.key = a.subject >= 0 ? xx_avalanche(h) : 0;
           sl_.fp = a.subject >= 0 ? fp_finish(f0, f1, f2, f3, t, slen) : 0;
@@ -236,10 +235,17 @@ __global__ void __launch_bounds__(rt::G::NT, rt::G::CTAS) k_rmdup_tile(RmdupTile
       }
       if (tid == 0) a.tile_cnt[tile] = n_own;
     }
-    __syncthreads();  // every thread is done with the stage before it is refilled
-    if (tid == 0) {
-      const u32 tn = tile + NSTAGE * gridDim.x;
-      if (tn < a.n_tiles) tile::issue_load<G>(a.in, n16, tn, sm.in[s], &sm.full[s]);
+    // Every thread is done with the stage before it is refilled -- but only the refilling warp waits for that: the
+    // others arrive and go on to scan the next tile (other stage) while the hashing lanes finish; nothing of this
+    // tile is overwritten before the next full barrier (inside scan_lines), which every thread joins.
+    if (warp != 0) {
+      tma::named_arrive(1, NT);
+    } else {
+      tma::named_sync(1, NT);
+      if (tid == 0) {
+        const u32 tn = tile + NSTAGE * gridDim.x;
+        if (tn < a.n_tiles) tile::issue_load<G>(a.in, n16, tn, sm.in[s], &sm.full[s]);
+      }
     }
   }
 }

@@ -50,14 +50,31 @@ def main():
                     "records_per_s": nrec / best, "dir": a.dir, "gpu_ms_in_call": tm.get("total_ms")}
             print(json.dumps(line), flush=True)
         if a.cpu:
+            import numpy as np
             import oracle
             threads = os.cpu_count() or 1
+            opts = {"Reverse": True, "Complement": True}
             sample = synth.fastq_reads(min(n, 256 << 20), seed=2)
             t0 = time.perf_counter()
-            nr, _ = oracle.run_mt("seq", sample.ctypes.data, sample.nbytes, {"Reverse": True, "Complement": True}, threads)
+            nr, _ = oracle.run_mt("seq", sample.ctypes.data, sample.nbytes, opts, threads)
             dt = time.perf_counter() - t0
             print(json.dumps({"scope": "cpu_port_in_memory", "cores": threads, "sample_bytes": int(sample.nbytes),
                               "gb_per_s_in": sample.nbytes / dt / 1e9, "records_per_s": nr / dt}), flush=True)
+            # the same port file -> file: read the file, transform on all threads, write the result (what the reference
+            # does around its operators: PlainFile ... FileStore)
+            best = None
+            for rep in range(2):
+                open(dst, "wb").close()
+                t0 = time.perf_counter()
+                arr = np.fromfile(src, dtype=np.uint8)
+                res = oracle.run_mt_full("seq", arr.ctypes.data, arr.nbytes, opts, threads)
+                res["data"].tofile(dst)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+                nr = res["records"]
+                del res, arr
+            print(json.dumps({"scope": "cpu_port_file_to_file", "cores": threads, "in_bytes": int(n), "best_s": best,
+                              "gb_per_s_in": n / best / 1e9, "records_per_s": nr / best}), flush=True)
     finally:
         for p in (src, dst):
             if os.path.exists(p):
