@@ -10,13 +10,13 @@
 // In that mode byte i of the output stream depends only on the record that covers byte i of the
 // input, and sits at the same offset.  So there is no inter-CTA dependency at all:
 //
-//   * persistent CTAs (512 threads, 3 per SM) walk 20 KiB tiles (+ 4 KiB halo) with a 2-stage ring filled by
-//     1-D TMA bulk loads;
+//   * persistent CTAs (512 threads, 4 per SM = 64 warps at 32 registers) walk 20 KiB tiles (+ 4 KiB halo) with a
+//     2-stage ring filled by 1-D TMA bulk loads;
 //   * a CTA finds the newlines of its region (16-byte shared-memory loads, SWAR zero-byte test, IDP.4A mask
 //     packing) and turns them into the list of line starts;
 //   * the records a tile owns (the ones that START inside it) are a chain of 4-line groups behind the first
-//     record line, so record r sits at lines kmin + 4r: one thread per record checks it against the grammar of
-//     SeqParser.Read, and the number of owned records falls out of the barrier that ends the check;
+//     record line, so record r sits at lines kmin + 4r: their number falls out of one counting barrier, and the
+//     lanes that rewrite a record check it against the grammar of SeqParser.Read first;
 //   * the sequence (reverse + 256-entry byte map) and the quality (reverse) of every owned record are
 //     rewritten IN PLACE in the stage buffer by 8 lanes, each producing consecutive 32-bit words with PRMT from
 //     a descending run of source words; the ragged first / last word of a segment is blended with the old word;
@@ -42,18 +42,19 @@ constexpr u32 PRE = 16;        // look-behind bytes in front of the tile
 constexpr u32 RCAP = 512;      // owned records per tile (slot stride)
 // CTA shape: NT threads, every lane scans CPL consecutive 16-byte chunks, so tile + halo = NT * CPL * 16 bytes.
 // 512 x 3 with 3 CTAs / SM and a 2-stage ring measured best of the seven shapes tried in round 1 (profiles/r1_ab_runs.txt).
-constexpr u32 NT = 512, CPL = 3, CTAS = 3, NSTAGE = 2, NWARP = NT / 32;
-constexpr u32 LCAP = 3072;                   // line starts per region
+constexpr u32 NT = 512, CPL = 3, NSTAGE = 2, NWARP = NT / 32;
 constexpr u32 T = NT * CPL * 16 - H;         // tile bytes
 constexpr u32 STAGE = PRE + T + H + 16;
 static_assert(T % 16 == 0 && STAGE % 16 == 0 && T + H < 65536 && NWARP <= 16 && CPL == 3, "tile geometry");
-struct Smem {
+template <u32 LCAP>            // line starts per region
+struct SmemT {
   u8 lut[256];                 // first, on a 256-byte boundary: lut4() forms addresses with PRMT instead of adds
   u8 in[NSTAGE][STAGE];
   u64 full[NSTAGE];
   u16 ls[LCAP + 8];            // line starts, ls[0] = 0
   u32 wtot[NWARP];
-  u32 bad, rescan;
+  u32 bad, rescan, kmin;
+  u32 bad_rec;                 // a record failed the grammar check of the transform pass (read by warp 0 behind it)
 };
 }  // namespace fq
 
@@ -255,9 +256,13 @@ __device__ __forceinline__ void record_inplace(u8 *d, u32 so, u32 sl, u32 qo, co
   }
 }
 
-// transform of all owned records of a tile, G lanes per record: record r opens at line kmin + 4r
-template <u32 G, u32 WPL>
-__device__ __forceinline__ void transform_tile(fq::Smem &sm, u8 *d, u32 kmin, u32 n_own, int reverse, int use_lut) {
+// Owned records of a tile, G lanes per record: record r opens at line kmin + 4r (all of them have their four lines in
+// the list).  The group checks its record against the grammar of SeqParser.Read -- "@h \n s \n + \n q \n" with
+// |s| == |q|, followed by a record line or the end of the file -- writes its element slot and rewrites it in place.
+// A record that is anything else raises sm.bad_rec (the block then goes to the general path) and is left alone.
+template <u32 G, u32 WPL, class SM, class IsStart>
+__device__ __forceinline__ void transform_tile(SM &sm, u8 *d, u32 kmin, u32 n_own, int reverse, int use_lut, u16 *slots,
+                                               bool eof, u32 lim, IsStart is_start) {
   const u32 g = threadIdx.x / G, gl = threadIdx.x % G;
   const Lut lut(sm.lut);
   for (u32 rb = 0; rb < n_own; rb += fq::NT / G) {  // uniform trip count per CTA
@@ -265,21 +270,35 @@ __device__ __forceinline__ void transform_tile(fq::Smem &sm, u8 *d, u32 kmin, u3
     u32 so = 0, sl = 0, qo = 0;
     if (r < n_own) {
       const u32 k = kmin + 4u * r;
-      so = sm.ls[k + 1];
-      sl = sm.ls[k + 2] - 1u - so;
-      qo = sm.ls[k + 3];
+      const u32 l0 = sm.ls[k], l1 = sm.ls[k + 1], l2 = sm.ls[k + 2], l3 = sm.ls[k + 3], l4 = sm.ls[k + 4];
+      const u32 ql = l4 - 1u - l3;
+      so = l1;
+      sl = l2 - 1u - l1;
+      qo = l3;
+      bool ok = d[l1] != '@';                             // the sequence line does not open a record
+      ok = ok && (l3 - l2 == 2) && d[l2] == '+';          // bare "+" line
+      ok = ok && sl == ql && !(sl > 0 && d[l1] == '+');   // a sequence line starting with '+' flips the parser
+      ok = ok && (is_start(l4) || (eof && l4 >= lim));    // next line opens a record, or the file ends here
+      if (!ok) {
+        sm.bad_rec = 1;  // (not sm.bad: slower warps may still be reading that one behind the counting barrier)
+        sl = 0;
+      } else if (gl == 0) {
+        slots[r] = (u16)l0;  // element slot, input order
+      }
     }
     if (reverse) {
       if (use_lut) record_inplace<true, true, G, WPL>(d, so, sl, qo, lut, gl);
       else record_inplace<true, false, G, WPL>(d, so, sl, qo, lut, gl);
-    } else {
+    } else if (use_lut) {
       record_inplace<false, true, G, WPL>(d, so, sl, qo, lut, gl);
     }
   }
 }
 
-__global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArgs a) {
+template <u32 CTAS, u32 LCAP>
+__global__ void __launch_bounds__(fq::NT, CTAS) k_fastq_inplace(FqInplaceArgs a) {
   using namespace fq;
+  typedef SmemT<LCAP> Smem;
 #ifndef BSK_EMU
   extern __shared__ __align__(256) unsigned char fq_raw_smem[];
   Smem *smp = reinterpret_cast<Smem *>(fq_raw_smem);
@@ -388,7 +407,7 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
         if ((int)lane >= off) inc += y;
       }
       if (lane == 31) sm.wtot[warp] = inc;
-      if (tid == 0) { sm.bad = 0; sm.rescan = 0; }
+      if (tid == 0) { sm.bad = 0; sm.rescan = 0; sm.kmin = 0xffffffffu; sm.bad_rec = 0; }
       __syncthreads();
       u32 base, n_nl;
       {
@@ -410,29 +429,24 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
           u32 t;
           if (mlo) { t = (u32)__ffs((int)mlo) - 1u; mlo &= mlo - 1u; }
           else { t = 32u + (u32)__ffs((int)mhi) - 1u; mhi &= mhi - 1u; }
-          sm.ls[k++] = (u16)(span + t + 1u);
+          const u32 p = span + t + 1u;
+          if (k < 8u && is_start(p)) atomicMin(&sm.kmin, k);  // first record line: one of lines 0..4 in a 4-line stream
+          sm.ls[k++] = (u16)p;
         }
         if (tid == 0) {
           sm.ls[0] = 0;
           if (virt) sm.ls[n_nl + 1] = (u16)(lim + 1);
+          if (lim > 0 && d[0] == '@' && (tile == 0 || (d[-1] == '\n' && !(d[-3] == '\n' && d[-2] == '+')))) sm.kmin = 0;
         }
       }
       n_lines = n_nl + (virt ? 1u : 0u);  // ls[0 .. n_lines] are valid
       __syncthreads();
 
-      // first record line of the region: in a 4-line stream it is one of lines 0..4 (every warp works it out)
-      {
-        bool st = false;
-        if (lane < 8u && lane <= n_lines) {
-          if (lane == 0) st = lim > 0 && d[0] == '@' && (tile == 0 || (d[-1] == '\n' && !(d[-3] == '\n' && d[-2] == '+')));
-          else st = is_start(sm.ls[lane]);
-        }
-        const u32 b = __ballot_sync(0xffffffffu, st);
-        kmin = b ? (u32)__ffs((int)b) - 1u : 0xffffffffu;
-      }
-      // Owned records = record lines that start inside the tile.  Each must be "@h \n s \n + \n q \n" with |s| == |q|
-      // and be followed by a record line (or the end of the file), so record r opens at line kmin + 4r: one thread
-      // per record, and the chain breaks (-> general path) at the first record that is anything else.
+      // Owned records = record lines that start inside the tile.  In a 4-line stream record r opens at line
+      // kmin + 4r (kmin: the first record line, found while the list was written); the chain is checked record by
+      // record in the transform pass below.  Here only: how many are there, and does the last one end inside the
+      // scanned part of the halo?
+      kmin = sm.kmin;
       bool own = false;
       if (kmin != 0xffffffffu) {
         const u32 k = kmin + 4u * tid;
@@ -440,19 +454,9 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
           const u32 l0 = sm.ls[k];
           if (l0 < T && l0 < lim) {  // (the entry behind the last line of the file is not a line)
             own = true;
-            if (k + 4 <= n_lines) {
-              const u32 l1 = sm.ls[k + 1], l2 = sm.ls[k + 2], l3 = sm.ls[k + 3], l4 = sm.ls[k + 4];
-              const u32 sl = l2 - 1 - l1, ql = l4 - 1 - l3;
-              bool ok = d[l1] != '@';                             // the sequence line does not open a record
-              ok = ok && (l3 - l2 == 2) && d[l2] == '+';          // bare "+" line
-              ok = ok && sl == ql && !(sl > 0 && d[l1] == '+');   // a sequence line starting with '+' flips the parser
-              ok = ok && (is_start(l4) || (eof && l4 >= lim));    // next line opens a record, or the file ends here
-              if (!ok) sm.bad = 1;
-              else a.slots[(size_t)tile * RCAP + tid] = (u16)l0;  // element slot, input order
-            } else if (slim < lim) {
-              sm.rescan = 1;  // the record ends beyond the scanned part of the halo
-            } else {
-              sm.bad = 1;     // longer than the halo, or truncated
+            if (k + 4 > n_lines) {
+              if (slim < lim) sm.rescan = 1;  // the record ends beyond the scanned part of the halo
+              else sm.bad = 1;                // longer than the halo, or truncated
             }
           }
         }
@@ -488,15 +492,16 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
       continue;  // uniform
     }
 
-    // ---- in-place transform
-    if (n_own && (a.reverse || a.use_lut)) {
+    // ---- grammar check + in-place transform, record by record
+    if (n_own) {
+      u16 *slots = a.slots + (size_t)tile * RCAP;
       if (a.group == 4) {
-        transform_tile<4, 10>(sm, d, kmin, n_own, a.reverse, a.use_lut);
+        transform_tile<4, 10>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       } else if (a.group == 8) {
-        if (a.wpl <= 5) transform_tile<8, 5>(sm, d, kmin, n_own, a.reverse, a.use_lut);
-        else transform_tile<8, 8>(sm, d, kmin, n_own, a.reverse, a.use_lut);
+        if (a.wpl <= 5) transform_tile<8, 5>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
+        else transform_tile<8, 8>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       } else {
-        transform_tile<32, 4>(sm, d, kmin, n_own, a.reverse, a.use_lut);
+        transform_tile<32, 4>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       }
     }
     // ---- owned byte range [lo, hi) -> out, same offsets: bulk store of the aligned body, ragged ends by warp 0.
@@ -509,7 +514,13 @@ __global__ void __launch_bounds__(fq::NT, fq::CTAS) k_fastq_inplace(FqInplaceArg
     } else {
       tma::named_sync(1, NT);
     }
-    if (warp == 0 && n_own > 0) {
+    if (warp == 0 && sm.bad_rec) {  // a record outside the grammar: the block goes to the general path
+      if (lane == 0) {
+        atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
+        const unsigned long long info = ((unsigned long long)tile << 32) | (1ull << 31) | ((u64)(n_own & 0x3ffu) << 16) | (n_lines & 0xffffu);
+        atomicMin((unsigned long long *)&a.st->counters[4], info);
+      }
+    } else if (warp == 0 && n_own > 0) {
       const u32 lo = sm.ls[kmin];
       const u32 hi = sm.ls[kmin + 4u * n_own];  // start of the next record == one past the '\n' that ends the last owned one
       const u32 lo16 = (lo + 15u) & ~15u, hi16 = hi & ~15u;
@@ -556,6 +567,25 @@ u32 fastq_inplace_tile_bytes() { return fq::T; }
 u32 fastq_inplace_tiles(u32 n) { return (n + fq::T - 1) / fq::T; }
 u32 fastq_inplace_slot_stride() { return fq::RCAP; }
 
+template <u32 CTAS, u32 LCAP>
+static void launch_fq(const FqInplaceArgs &a, int n_sm, cudaStream_t s) {
+  const size_t smem = sizeof(fq::SmemT<LCAP>) + 16;
+#ifndef BSK_EMU
+  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(k_fastq_inplace<CTAS, LCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set[dev] = true;
+  }
+#endif
+  u32 grid = (u32)n_sm * CTAS;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid == 0) return;
+  BSK_LAUNCH((k_fastq_inplace<CTAS, LCAP>), grid, fq::NT, smem, s, a);
+}
+
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
                    int use_lut, int group, u32 max_seg, u32 scan_halo, int n_sm, cudaStream_t s) {
   FqInplaceArgs a;
@@ -573,21 +603,11 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   a.wpl = max_seg <= 154 ? 5 : 8;
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > fq::H ? fq::H : scan_halo);
-  const size_t smem = sizeof(fq::Smem) + 16;
-#ifndef BSK_EMU
-  // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(k_fastq_inplace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set[dev] = true;
-  }
-#endif
-  u32 grid = (u32)n_sm * fq::CTAS;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (grid == 0) return;
-  BSK_LAUNCH(k_fastq_inplace, grid, fq::NT, smem, s, a);
+  // 4 CTAs / SM (64 warps, 32 registers per thread, 2048 line starts per region): 0.658 ms per GiB against 0.707 ms
+  // with 3 CTAs / SM (40 registers, 3072 line starts), which BSK_FQ_CTAS=3 still selects (profiles/r2_experiments.txt)
+  static const int ctas = getenv("BSK_FQ_CTAS") ? atoi(getenv("BSK_FQ_CTAS")) : 4;
+  if (ctas == 3) launch_fq<3, 3072>(a, n_sm, s);
+  else launch_fq<4, 2048>(a, n_sm, s);
 }
 
 void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, u64 cap,
