@@ -8,10 +8,10 @@
 //
 // The reference makes (#patterns x 2) passes over every sequence and builds a fresh reverse complement per pattern.
 // Here the input is read once, newlines in place:
-//   * persistent CTAs (4 per SM) walk 23 KiB tiles with a 1 KiB look-behind, staged by 1-D TMA bulk loads;
+//   * persistent CTAs (512 threads, 4 per SM) walk 23 KiB tiles with a 1 KiB look-behind, staged by 1-D TMA bulk loads;
 //   * a SWAR newline scan gives every lane its newline masks (-> sequence coordinates) and finds the header lines
 //     (a '>' that follows a newline), whose bytes are overwritten in the stage buffer so that no window spans them;
-//   * every lane rolls the 2-bit code of the last L bases over its 96 bytes (32 bytes of warm-up), skipping newlines;
+//   * every lane rolls the 2-bit code of the last L bases over its 48 bytes (16 bytes of warm-up), skipping newlines;
 //     each window probes a two-hash Bloom bitmap of the needle codes in shared memory (patterns and, for the '-'
 //     strand, reverse(pair(pattern)) -- matched on the forward strand, bigseqkit-lib/locate.go:669-766); the rare
 //     positives are parked in a shared-memory queue and confirmed by the whole CTA in an exact table in L2;
@@ -27,20 +27,22 @@ namespace bsk {
 namespace k {
 
 namespace lt {
-constexpr u32 NT = 256;                  // threads per CTA
-constexpr u32 SPAN = 96;                 // bytes per lane
+constexpr u32 NT = 512;                  // threads per CTA (4 CTAs / SM = 64 warps at 32 registers)
+constexpr u32 SPAN = 48;                 // bytes per lane
+constexpr u32 NCH = SPAN / 16;           // 16-byte chunks per lane
 constexpr u32 REGION = NT * SPAN;        // staged bytes per tile
-constexpr u32 LBL = 11;                  // look-behind lanes
+constexpr u32 LBL = 22;                  // look-behind lanes (all in warp 0)
 constexpr u32 LB = LBL * SPAN;           // 1056 look-behind bytes
 constexpr u32 T = REGION - LB;           // 23520 owned bytes per tile
-constexpr u32 WU = 32;                   // warm-up bytes in front of a lane's span
+constexpr u32 WU = 16;                   // warm-up bytes in front of a lane's span (>= L - 1 symbols unless two newlines fall inside)
 constexpr u32 HDR_MAX = 960;             // longest header line accepted (must stay below LB - WU)
 constexpr u32 NWARP = NT / 32;
 constexpr u32 FBITS = 17;                // Bloom bitmap: 2^17 bits = 16 KiB, two probes per window
 constexpr u32 FWORDS = (1u << FBITS) / 32;
 constexpr u32 QCAP = 1024;               // candidates per tile parked for the confirmation pass
 constexpr u32 CTAS = 4;                  // CTAs per SM: one stage buffer each, the other CTAs hide the load
-static_assert(T % 16 == 0 && LB % 16 == 0 && SPAN % 16 == 0 && WU % 16 == 0 && HDR_MAX + WU < LB, "tile geometry");
+static_assert(T % 16 == 0 && LB % 16 == 0 && SPAN % 16 == 0 && WU % 16 == 0 && HDR_MAX + WU < LB && LBL < 32 && (NCH == 3 || NCH == 6),
+              "tile geometry");
 
 // byte classes of the rolling pass
 constexpr u8 C_BASE = 8;    // valid base (code in bits 0-1)
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
   const u32 n = a.n, n16 = n & ~15u;
   const u32 L = a.L;
 
-  s_lut[tid] = a.lut[tid];
+  if (tid < 256) s_lut[tid] = a.lut[tid];
   for (u32 i = tid; i < FWORDS; i += NT) s_filter[i] = a.filter[i];
   if (tid == 0) {
     tma::mbar_init(&sm.full, 1);
@@ -143,9 +145,9 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
     const u32 span0 = tid * SPAN;
     u32 m[3];
     {
-      u32 m16[6];
+      u32 m16[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (u32 j = 0; j < 6; j++) {
+      for (u32 j = 0; j < NCH; j++) {
         const uint4 v = *reinterpret_cast<const uint4 *>(d + span0 + j * 16u);
         u32 lo = __dp4a(lt_nl_flags(v.x), 0x08040201u, 0u);
         lo = __dp4a(lt_nl_flags(v.y), 0x80402010u, lo);
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
       }
       const uint4 *vp = reinterpret_cast<const uint4 *>(d + span0);
 #pragma unroll 1
-      for (u32 v = 0; v < SPAN / 16; v++) {
+      for (u32 v = 0; v < NCH; v++) {
         const uint4 q = vp[v];
         const u32 w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll

@@ -19,7 +19,7 @@ namespace bsk {
 namespace k {
 
 namespace rt {
-typedef tile::Geo<512, 3, 3, 2, 3072> G;
+typedef tile::Geo<512, 3, 3, 2, 3072> G;  // (4 CTAs / SM at 32 registers measured no faster: 0.855 vs 0.823 ms per GiB)
 constexpr u32 RCAP = 192;  // record slots per tile (20 KiB tile: records of >= 107 bytes on average)
 
 struct Smem {

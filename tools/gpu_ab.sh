@@ -1,4 +1,8 @@
 mkdir -p gpurun_out
-BSK_FQ_CTAS=4 timeout 600 python -m pytest tests/test_fused_path.py tests/test_properties_gpu.py -m gpu -x -q 2>&1 | tail -2
-for c in 3 4 3 4; do BSK_FQ_CTAS=$c timeout 300 python bench.py --steps 10 --warmup 3 --ops none --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print('ctas $c', 'ms_per_step', round(d['ms_per_step'],4), 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'frac', round(d['roofline']['frac'],4))"; done
+timeout 900 python -m pytest tests/test_locate_tile.py tests/test_parity_match.py tests/test_parity_rmdup.py tests/test_fullsize_gpu.py tests/test_exchange.py -m gpu -x -q 2>&1 | tail -2
+timeout 600 python bench.py --ops-only --ops rmdup,locate --steps 5 --no-e2e > gpurun_out/r2t_ops.json 2> gpurun_out/r2t_ops.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2t_ops.json').read().strip().splitlines()[-1])
+for k,v in d['ops'].items(): print(k, round(v['ms_per_step'],3), round(v['roofline']['kernel_ms'],3), round(v['roofline']['frac'],3), round(v['roofline']['whole_step_frac'],3), v['parity']['match'])
+PY
+tail -2 gpurun_out/r2t_ops.err
