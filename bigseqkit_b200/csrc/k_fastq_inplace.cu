@@ -10,8 +10,8 @@
 // In that mode byte i of the output stream depends only on the record that covers byte i of the
 // input, and sits at the same offset.  So there is no inter-CTA dependency at all:
 //
-//   * persistent CTAs (512 threads, 4 per SM = 64 warps at 32 registers) walk 20 KiB tiles (+ 4 KiB halo) with a
-//     2-stage ring filled by 1-D TMA bulk loads;
+//   * persistent CTAs (512 threads, 4 per SM = 64 warps at 32 registers; other shapes stay selectable for A/B runs
+//     with BSK_FQ_SHAPE) walk 20 KiB tiles (+ 4 KiB halo) with a 2-stage ring filled by 1-D TMA bulk loads;
 //   * a CTA finds the newlines of its region (16-byte shared-memory loads, SWAR zero-byte test, IDP.4A mask
 //     packing) and turns them into the list of line starts;
 //   * the records a tile owns (the ones that START inside it) are a chain of 4-line groups behind the first
@@ -39,23 +39,31 @@ namespace k {
 namespace fq {
 constexpr u32 H = 4096;        // halo bytes (longest record the kernel accepts, roughly)
 constexpr u32 PRE = 16;        // look-behind bytes in front of the tile
-constexpr u32 RCAP = 512;      // owned records per tile (slot stride)
+constexpr u32 RCAP = 1024;     // owned records per tile (slot stride)
 // CTA shape: NT threads, every lane scans CPL consecutive 16-byte chunks, so tile + halo = NT * CPL * 16 bytes.
-// 512 x 3 with 3 CTAs / SM and a 2-stage ring measured best of the seven shapes tried in round 1 (profiles/r1_ab_runs.txt).
-constexpr u32 NT = 512, CPL = 3, NSTAGE = 2, NWARP = NT / 32;
-constexpr u32 T = NT * CPL * 16 - H;         // tile bytes
-constexpr u32 STAGE = PRE + T + H + 16;
-static_assert(T % 16 == 0 && STAGE % 16 == 0 && T + H < 65536 && NWARP <= 16 && CPL == 3, "tile geometry");
-template <u32 LCAP>            // line starts per region
-struct SmemT {
-  u8 lut[256];                 // first, on a 256-byte boundary: lut4() forms addresses with PRMT instead of adds
-  u8 in[NSTAGE][STAGE];
-  u64 full[NSTAGE];
-  u16 ls[LCAP + 8];            // line starts, ls[0] = 0
-  u32 wtot[NWARP];
-  u32 bad, rescan, kmin;
-  u32 bad_rec;                 // a record failed the grammar check of the transform pass (read by warp 0 behind it)
+constexpr u32 CPL = 3, NSTAGE = 2;
+template <u32 NT_, u32 CTAS_, u32 LCAP_>
+struct Cfg {
+  static constexpr u32 NT = NT_, CTAS = CTAS_, LCAP = LCAP_;  // threads, CTAs per SM, line starts per region
+  static constexpr u32 NWARP = NT / 32;
+  static constexpr u32 T = NT * CPL * 16 - H;  // tile bytes
+  static constexpr u32 STAGE = PRE + T + H + 16;
+  static_assert(T % 16 == 0 && STAGE % 16 == 0 && T + H < 65536 && NWARP <= 32 && NT <= RCAP, "tile geometry");
+  struct Smem {
+    u8 lut[256];                 // first, on a 256-byte boundary: lut4() forms addresses with PRMT instead of adds
+    u8 in[NSTAGE][STAGE];
+    u64 full[NSTAGE];
+    u16 ls[LCAP + 8];            // line starts, ls[0] = 0
+    u32 wtot[NWARP];
+    u32 bad, rescan, kmin;
+    u32 bad_rec;                 // a record failed the grammar check of the transform pass (read by warp 0 behind it)
+  };
 };
+typedef Cfg<512, 4, 2048> CfgA;  // 64 warps / SM at 32 registers, 20 KiB tiles: the default
+typedef Cfg<512, 3, 3072> CfgB;  // 48 warps / SM at 40 registers
+typedef Cfg<256, 8, 1024> CfgC;  // 8 KiB tiles, 8 independent CTAs / SM
+typedef Cfg<384, 5, 1536> CfgD;  // 14 KiB tiles, 5 CTAs / SM
+typedef Cfg<1024, 2, 4096> CfgE; // 44 KiB tiles, 2 CTAs / SM of 32 warps
 }  // namespace fq
 
 struct FqInplaceArgs {
@@ -260,12 +268,12 @@ __device__ __forceinline__ void record_inplace(u8 *d, u32 so, u32 sl, u32 qo, co
 // the list).  The group checks its record against the grammar of SeqParser.Read -- "@h \n s \n + \n q \n" with
 // |s| == |q|, followed by a record line or the end of the file -- writes its element slot and rewrites it in place.
 // A record that is anything else raises sm.bad_rec (the block then goes to the general path) and is left alone.
-template <u32 G, u32 WPL, class SM, class IsStart>
+template <u32 NT, u32 G, u32 WPL, class SM, class IsStart>
 __device__ __forceinline__ void transform_tile(SM &sm, u8 *d, u32 kmin, u32 n_own, int reverse, int use_lut, u16 *slots,
                                                bool eof, u32 lim, IsStart is_start) {
   const u32 g = threadIdx.x / G, gl = threadIdx.x % G;
   const Lut lut(sm.lut);
-  for (u32 rb = 0; rb < n_own; rb += fq::NT / G) {  // uniform trip count per CTA
+  for (u32 rb = 0; rb < n_own; rb += NT / G) {  // uniform trip count per CTA
     const u32 r = rb + g;
     u32 so = 0, sl = 0, qo = 0;
     if (r < n_own) {
@@ -295,10 +303,11 @@ __device__ __forceinline__ void transform_tile(SM &sm, u8 *d, u32 kmin, u32 n_ow
   }
 }
 
-template <u32 CTAS, u32 LCAP>
-__global__ void __launch_bounds__(fq::NT, CTAS) k_fastq_inplace(FqInplaceArgs a) {
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::CTAS) k_fastq_inplace(FqInplaceArgs a) {
   using namespace fq;
-  typedef SmemT<LCAP> Smem;
+  constexpr u32 NT = C::NT, NWARP = C::NWARP, T = C::T, LCAP = C::LCAP;
+  typedef typename C::Smem Smem;
 #ifndef BSK_EMU
   extern __shared__ __align__(256) unsigned char fq_raw_smem[];
   Smem *smp = reinterpret_cast<Smem *>(fq_raw_smem);
@@ -411,14 +420,15 @@ __global__ void __launch_bounds__(fq::NT, CTAS) k_fastq_inplace(FqInplaceArgs a)
       __syncthreads();
       u32 base, n_nl;
       {
-        u32 x = (lane & 15u) < NWARP ? sm.wtot[lane & 15u] : 0u;
+        constexpr u32 W = NWARP <= 16 ? 16 : 32;  // lanes that scan the warp totals
+        u32 x = (lane & (W - 1u)) < NWARP ? sm.wtot[lane & (W - 1u)] : 0u;
 #pragma unroll
-        for (int off = 1; off < 16; off <<= 1) {
-          const u32 y = __shfl_up_sync(0xffffffffu, x, off, 16);
-          if ((int)(lane & 15u) >= off) x += y;
+        for (int off = 1; off < (int)W; off <<= 1) {
+          const u32 y = __shfl_up_sync(0xffffffffu, x, off, W);
+          if ((int)(lane & (W - 1u)) >= off) x += y;
         }
-        n_nl = __shfl_sync(0xffffffffu, x, 15);
-        base = __shfl_sync(0xffffffffu, x, (warp + 15u) & 15u);
+        n_nl = __shfl_sync(0xffffffffu, x, W - 1);
+        base = __shfl_sync(0xffffffffu, x, (warp + W - 1u) & (W - 1u));
         if (warp == 0) base = 0;
       }
       const bool virt = eof && slim == lim && lim > 0 && d[lim - 1] != '\n';  // unterminated last line
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(fq::NT, CTAS) k_fastq_inplace(FqInplaceArgs a)
         sm.bad = 1;  // eight lines without a record line: not a 4-line stream
       }
       n_own = (u32)__syncthreads_count(own);
-      bad = sm.bad != 0 || n_own >= RCAP;
+      bad = sm.bad != 0 || n_own >= NT;  // (a thread per chain position: NT of them may not be all)
       if (tile == 0 && kmin != 0) bad = true;  // the file must open with a marked record
       const bool rescan = sm.rescan != 0;
       if (bad || !rescan || hs >= H) {
@@ -496,12 +506,12 @@ __global__ void __launch_bounds__(fq::NT, CTAS) k_fastq_inplace(FqInplaceArgs a)
     if (n_own) {
       u16 *slots = a.slots + (size_t)tile * RCAP;
       if (a.group == 4) {
-        transform_tile<4, 10>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
+        transform_tile<NT, 4, 10>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       } else if (a.group == 8) {
-        if (a.wpl <= 5) transform_tile<8, 5>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
-        else transform_tile<8, 8>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
+        if (a.wpl <= 5) transform_tile<NT, 8, 5>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
+        else transform_tile<NT, 8, 8>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       } else {
-        transform_tile<32, 4>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
+        transform_tile<NT, 32, 4>(sm, d, kmin, n_own, a.reverse, a.use_lut, slots, eof, lim, is_start);
       }
     }
     // ---- owned byte range [lo, hi) -> out, same offsets: bulk store of the aligned body, ragged ends by warp 0.
@@ -563,27 +573,41 @@ __global__ void k_fastq_elem_expand(const u32 *__restrict__ tile_cnt, const u64 
   }
 }
 
-u32 fastq_inplace_tile_bytes() { return fq::T; }
-u32 fastq_inplace_tiles(u32 n) { return (n + fq::T - 1) / fq::T; }
+// CTA shape of the process: 512 x 4 unless BSK_FQ_SHAPE says otherwise (A/B runs: profiles/r2_experiments.txt)
+static int fq_shape() {
+  const char *e = getenv("BSK_FQ_SHAPE");
+  const int v = e ? atoi(e) : 0;
+  return v >= 0 && v <= 3 ? v : 0;
+}
+u32 fastq_inplace_tile_bytes() {
+  switch (fq_shape()) {
+    case 1: return fq::CfgB::T;
+    case 2: return fq::CfgC::T;
+    case 3: return fq::CfgD::T;
+    case 4: return fq::CfgE::T;
+    default: return fq::CfgA::T;
+  }
+}
+u32 fastq_inplace_tiles(u32 n) { return (n + fastq_inplace_tile_bytes() - 1) / fastq_inplace_tile_bytes(); }
 u32 fastq_inplace_slot_stride() { return fq::RCAP; }
 
-template <u32 CTAS, u32 LCAP>
+template <class C>
 static void launch_fq(const FqInplaceArgs &a, int n_sm, cudaStream_t s) {
-  const size_t smem = sizeof(fq::SmemT<LCAP>) + 16;
+  const size_t smem = sizeof(typename C::Smem) + 16;
 #ifndef BSK_EMU
   // the opt-in to > 48 KiB of dynamic shared memory is per device (a process may hold ctxs on several GPUs)
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaFuncSetAttribute(k_fastq_inplace<CTAS, LCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_fastq_inplace<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set[dev] = true;
   }
 #endif
-  u32 grid = (u32)n_sm * CTAS;
+  u32 grid = (u32)n_sm * C::CTAS;
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid == 0) return;
-  BSK_LAUNCH((k_fastq_inplace<CTAS, LCAP>), grid, fq::NT, smem, s, a);
+  BSK_LAUNCH(k_fastq_inplace<C>, grid, C::NT, smem, s, a);
 }
 
 void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u16 *slots, DevStatus *st, int reverse,
@@ -603,11 +627,13 @@ void fastq_inplace(const u8 *in, u32 n, u8 *out, const u8 *lut, u32 *tile_cnt, u
   a.wpl = max_seg <= 154 ? 5 : 8;
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > fq::H ? fq::H : scan_halo);
-  // 4 CTAs / SM (64 warps, 32 registers per thread, 2048 line starts per region): 0.658 ms per GiB against 0.707 ms
-  // with 3 CTAs / SM (40 registers, 3072 line starts), which BSK_FQ_CTAS=3 still selects (profiles/r2_experiments.txt)
-  static const int ctas = getenv("BSK_FQ_CTAS") ? atoi(getenv("BSK_FQ_CTAS")) : 4;
-  if (ctas == 3) launch_fq<3, 3072>(a, n_sm, s);
-  else launch_fq<4, 2048>(a, n_sm, s);
+  switch (fq_shape()) {
+    case 1: launch_fq<fq::CfgB>(a, n_sm, s); break;
+    case 2: launch_fq<fq::CfgC>(a, n_sm, s); break;
+    case 3: launch_fq<fq::CfgD>(a, n_sm, s); break;
+    case 4: launch_fq<fq::CfgE>(a, n_sm, s); break;
+    default: launch_fq<fq::CfgA>(a, n_sm, s);
+  }
 }
 
 void fastq_elem_expand(const u32 *tile_cnt, const u64 *tile_base, const u16 *slots, u64 *elem_off, u32 n_tiles, u64 cap,

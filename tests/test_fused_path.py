@@ -212,6 +212,20 @@ def test_records_that_start_on_a_tile_boundary(lib):
     assert r.data == exp[0] and list(r.elem_off) == exp[1]
 
 
+@pytest.mark.parametrize("shape", ["1", "2", "3", "4"])
+def test_inplace_cta_shapes(lib, monkeypatch, shape):
+    # the CTA shapes kept for A/B runs (BSK_FQ_SHAPE: 512 x 3, 256 x 8, 384 x 5, 1024 x 2) give the same bytes as the default
+    if lib.path.endswith("libbsk_emu.so") and shape == "3":
+        pytest.skip("covered on the GPU")
+    monkeypatch.setenv("BSK_FQ_SHAPE", shape)
+    opts = {"Reverse": True, "Complement": True}
+    for name in ("reads150", "len250", "rec64_tile_aligned", "short_then_long", "no_final_newline", "rec48_many_lines", "tiny_file"):
+        data = inplace_inputs()[name]
+        exp = oracle.seq(data, opts)
+        r, t = run(lib, data, opts)
+        assert r.data == exp[0] and list(r.elem_off) == exp[1], (name, shape)
+
+
 @pytest.mark.parametrize("group", ["8", "32"])
 @pytest.mark.parametrize("opts", [{"Reverse": True, "Complement": True}, {"Reverse": True}, {"Complement": True}], ids=str)
 def test_inplace_lane_groups(lib, monkeypatch, group, opts):
