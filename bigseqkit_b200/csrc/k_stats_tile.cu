@@ -19,17 +19,19 @@ namespace k {
 
 namespace st {
 constexpr u32 HB = 4224;  // histogram bins: a record (and so its sequence) is shorter than the halo + slack
-typedef tile::Geo<512, 3, 3, 2, 3072> G;
+typedef tile::Geo<512, 3, 3, 2, 2048> G;
 constexpr u32 ICAP = G::LCAP;  // work items (sequence / quality lines) per tile
 
-// -a needs the work-item list (12 KiB): 2 CTAs / SM; without it 3 CTAs / SM fit
+// The shared-memory histogram holds the lengths below HBS (reads); longer ones go straight to the global histogram.
+// Without -a 4 CTAs / SM fit (64 warps at 32 registers); -a needs the work-item list (8 KiB): 3 CTAs / SM.
+constexpr u32 HBS = 960;
 template <bool ALL>
 struct Smem {
   u8 in[G::NSTAGE][G::STAGE];
   u64 full[G::NSTAGE];
   u16 ls[G::LCAP + 8];
   u32 item[ALL ? ICAP : 1];  // a (15 bits) | len (15 bits) << 15 | kind << 30   (kind 1 = quality line)
-  u32 hist[HB];
+  u32 hist[HBS];
   u32 wtot[G::NWARP];
   u32 bad, rescan, n_item, n_rec;
   unsigned long long acc[3];  // q20, q30, gaps of this CTA
@@ -49,26 +51,27 @@ struct StatsTileArgs {
   u32 scan_halo;
 };
 
-// number of bytes of w (4 packed bytes) that are >= c, c < 128; exact for every byte value
-__device__ __forceinline__ u32 count_ge4(u32 w, u32 c4) {
+// flags (0x80 per byte) of the bytes of w (4 packed bytes) that are >= c, c < 128; exact for every byte value
+__device__ __forceinline__ u32 ge_flags4(u32 w, u32 c4) {
   const u32 t = ((w & 0x7f7f7f7fu) | 0x80808080u) - c4;  // bit 7 of a byte survives iff its low 7 bits >= c
-  return (u32)__popc((t | w) & 0x80808080u);
+  return (t | w) & 0x80808080u;
 }
 
 template <bool ALL>
-__global__ void __launch_bounds__(st::G::NT, ALL ? 2 : 3) k_stats_tile(StatsTileArgs a) {
+__global__ void __launch_bounds__(st::G::NT, ALL ? 3 : 4) k_stats_tile(StatsTileArgs a) {
   using namespace st;
   typedef st::Smem<ALL> Smem;
   using tile::H;
   using tile::PRE;
   constexpr u32 NT = G::NT, T = G::T, NSTAGE = G::NSTAGE;
+  constexpr u32 HS = HBS;  // bins of the shared-memory histogram
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const u32 n = a.n, n16 = n & ~15u;
   const bool fq = a.fastq != 0;
 
-  for (u32 i = tid; i < HB; i += NT) sm.hist[i] = 0;
+  for (u32 i = tid; i < HS; i += NT) sm.hist[i] = 0;
   if (tid == 0) {
     for (u32 s = 0; s < NSTAGE; s++) tma::mbar_init(&sm.full[s], 1);
     tma::fence_barrier_init();
@@ -146,9 +149,13 @@ __global__ void __launch_bounds__(st::G::NT, ALL ? 2 : 3) k_stats_tile(StatsTile
       const u32 leader = (u32)__ffs((int)bal) - 1u;
       const u32 first = __shfl_sync(0xffffffffu, slen, (int)leader);
       if (__all_sync(0xffffffffu, !valid || slen == first)) {
-        if (lane == leader) atomicAdd(&sm.hist[first], (u32)__popc(bal));
+        if (lane == leader) {
+          if (first < HS) atomicAdd(&sm.hist[first], (u32)__popc(bal));
+          else atomicAdd((unsigned long long *)&a.hist[first], (unsigned long long)__popc(bal));
+        }
       } else if (valid) {
-        atomicAdd(&sm.hist[slen], 1u);
+        if (slen < HS) atomicAdd(&sm.hist[slen], 1u);
+        else atomicAdd((unsigned long long *)&a.hist[slen], 1ull);
       }
     };
     // with -a the sequence / quality lines of a complete owned record become work items
@@ -228,37 +235,39 @@ __global__ void __launch_bounds__(st::G::NT, ALL ? 2 : 3) k_stats_tile(StatsTile
     if (bad) {
       if (tid == 0) atomicAdd((unsigned long long *)&a.st->counters[0], 1ull);
     } else if (ALL) {
-      // ---- work items: 8 lanes per line, 4 bytes per lane and step
+      // ---- work items: 4 lanes per line (a 150-byte line is 10-11 chunks: three steps), one aligned 16-byte chunk per lane and step.  The bytes of the chunk that
+      // belong to the line are selected by a flag mask (bit 7 of byte i set iff lo <= i < hi) that is ANDed with the
+      // flags of the byte tests, so no byte is masked itself.
       const u32 n_item = sm.n_item;
-      const u32 g = tid >> 3, gl = tid & 7u;
-      const u32 *w32 = reinterpret_cast<const u32 *>(d);
-      for (u32 ib = g; ib < n_item; ib += NT / 8) {
+      const u32 g = tid >> 2, gl = tid & 3u;
+      for (u32 ib = g; ib < n_item; ib += NT / 4) {
         const u32 e = sm.item[ib];
         const u32 p = e & 0x7fffu, L = (e >> 15) & 0x7fffu, kind = e >> 30;
-        const u32 w0 = p >> 2, w1 = (p + L + 3u) >> 2;  // words [w0, w1) cover the line
-        for (u32 w = w0 + gl; w < w1; w += 8) {
-          u32 v = w32[w];
-          if (w == w0 || w + 1 == w1) {
-            // bytes outside [p, p+L) become a neutral value: 0 for quality (below every threshold), '@' for sequence
-            const u32 b0 = w << 2;
-            u32 m = 0xffffffffu;
-            if (b0 < p) m &= 0xffffffffu << (8u * (p - b0));
-            if (b0 + 4u > p + L) m &= 0xffffffffu >> (8u * (b0 + 4u - (p + L)));
-            v = kind ? (v & m) : ((v & m) | (0x40404040u & ~m));
-          }
-          if (kind) {
-            q20 += count_ge4(v, c20);
-            q30 += count_ge4(v, c30);
-          } else if (!a.gap_below_40 || (((v | (v >> 1)) & 0x40404040u) != 0x40404040u)) {
-            // only words holding a byte below 0x40 can hold one of the (sub-'@') gap letters
-            u32 f = 0;
+        const u32 c1 = (p + L + 15u) & ~15u;
+        for (u32 c = (p & ~15u) + 16u * gl; c < c1; c += 64u) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(d + c);
+          const u32 lo = p > c ? p - c : 0u, hi = p + L - c < 16u ? p + L - c : 16u;
+          const u32 lo4 = lo * 0x01010101u, hi4 = hi * 0x01010101u;
+          const u32 w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (j < a.n_gap) {
-                const u32 x = v ^ a.gap[j];
-                f |= ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;  // distinct letters: disjoint flags
-              }
-            gaps += (u32)__popc(f);
+          for (u32 k2 = 0; k2 < 4; k2++) {
+            const u32 w = w4[k2];
+            const u32 idx = (0x03020100u + k2 * 0x04040404u) | 0x80808080u;  // byte indices of the word in the chunk
+            const u32 m7 = (idx - lo4) & ~(idx - hi4) & 0x80808080u;
+            if (kind) {
+              q20 += (u32)__popc(ge_flags4(w, c20) & m7);
+              q30 += (u32)__popc(ge_flags4(w, c30) & m7);
+            } else if (!a.gap_below_40 || (((w | (w >> 1)) & 0x40404040u) != 0x40404040u)) {
+              // only words holding a byte below 0x40 can hold one of the (sub-'@') gap letters
+              u32 f = 0;
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                if (j < a.n_gap) {
+                  const u32 x = w ^ a.gap[j];
+                  f |= ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;  // distinct letters: disjoint flags
+                }
+              gaps += (u32)__popc(f & m7);
+            }
           }
         }
       }
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(st::G::NT, ALL ? 2 : 3) k_stats_tile(StatsTile
     }
   }
   __syncthreads();
-  for (u32 i = tid; i < HB; i += NT) {
+  for (u32 i = tid; i < HS; i += NT) {
     const u32 c = sm.hist[i];
     if (c) atomicAdd((unsigned long long *)&a.hist[i], (unsigned long long)c);
   }
@@ -317,7 +326,7 @@ void stats_tile(const u8 *in, u32 n, u64 *hist, DevStatus *st, int fastq, int al
     if (gap_letters[i] >= 0x40) a.gap_below_40 = 0;
   scan_halo = (scan_halo + 15u) & ~15u;
   a.scan_halo = scan_halo < 256u ? 256u : (scan_halo > tile::H ? tile::H : scan_halo);
-  const int ctas = all ? 2 : 3;
+  const int ctas = all ? 3 : 4;
   u32 grid = (u32)n_sm * ctas;
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid == 0) return;

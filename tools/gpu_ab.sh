@@ -1,6 +1,8 @@
-for c in 0 4 1; do BSK_FQ_COPYONLY=1 BSK_FQ_SHAPE=$c timeout 300 python bench.py --steps 10 --warmup 3 --ops none --no-cpu-baseline --no-e2e --no-parity 2>&1 | python -c "
-import sys,json
-t=sys.stdin.read()
-try:
-    d=json.loads(t.strip().splitlines()[-1]); print('copy-only shape $c', 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'frac', round(d['roofline']['frac'],4), 'ms_per_step', round(d['ms_per_step'],4))
-except Exception as e: print('fail', t[-300:])"; done
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_stats_tile.py -m gpu -x -q 2>&1 | tail -2
+timeout 600 python bench.py --ops-only --ops stats,stats_all --steps 10 --no-e2e > gpurun_out/r2v_stats.json 2> gpurun_out/r2v_stats.err; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2v_stats.json').read().strip().splitlines()[-1])
+for k,v in d['ops'].items(): print(k, round(v['ms_per_step'],3), round(v['roofline']['kernel_ms'],4), round(v['roofline']['frac'],3), v['parity']['match'])
+PY
+tail -2 gpurun_out/r2v_stats.err
