@@ -330,6 +330,11 @@ bool parse_and_validate(Op op, const char *json, Opts &o, std::string &err, int 
         if (f == 6) { o.frames = {1, 2, 3, -1, -2, -3}; break; }
         o.frames.push_back((int)f);
       }
+      if (o.frames.size() > 66) {  // the device-side frame list holds 66 entries (the reference takes any number of repeats)
+        code = BSK_ERR_UNSUPPORTED;
+        err = "translate: more than 66 frame values are outside the accelerated path";
+        return false;
+      }
       break;
     }
     case OP_LOCATE: {  // bigseqkit-lib/locate.go:33-193

@@ -894,7 +894,7 @@ static int parse_frames(const char *csv, int *frames, char *err) { /* lib/transl
     if (k == 0 || *endp) { snprintf(err, 512, "invalid frame(s): %s. available: 1, 2, 3, -1, -2, -3, and 6 for all. multiple frames should be separated by comma", tok); return -1; }
     if (!(f == 1 || f == 2 || f == 3 || f == -1 || f == -2 || f == -3 || f == 6)) { snprintf(err, 512, "invalid frame: %ld. available: 1, 2, 3, -1, -2, -3, and 6 for all", f); return -1; }
     if (f == 6) { int all6[6] = {1, 2, 3, -1, -2, -3}; memcpy(frames, all6, sizeof all6); return 6; }
-    if (nf < 64) frames[nf++] = (int)f;
+    if (nf < 4096) frames[nf++] = (int)f;  /* the reference takes any number of repeats; 4096 is this restatement's bound */
   }
   return nf;
 }
@@ -904,7 +904,7 @@ int orc_translate(const uint8_t *data, size_t n, const orc_opts *o, orc_out *out
   if (ab < 0) return -1;
   const gcode_t *t = gcode_find(o->TranslTable);
   if (!t) { snprintf(out->err, 512, "invalid translate table: %d", o->TranslTable); return -1; }
-  int frames[64];
+  int frames[4096];
   int nf = parse_frames(o->Frame ? o->Frame : "1", frames, out->err);
   if (nf < 0) return -1;
   parser_t p; parser_init(&p, data, n, ab, o);

@@ -79,3 +79,13 @@ def test_translate_wrapped_fasta_both_squeeze_paths(lib, monkeypatch):
             if env:
                 monkeypatch.delenv("BSK_NO_UNIFORM_SQUEEZE")
             assert got[0] == exp[0] and list(got[1]) == list(exp[1]), (name, env)
+
+
+def test_more_than_66_frames_is_refused(lib):
+    # the device-side frame list holds 66 entries; a longer list is an explicit error, not a silently shorter output
+    from bigseqkit_b200.api import BskError
+    with pytest.raises(BskError):
+        Operator("Translate", {"Frame": ["1"] * 67}, lib=lib)
+    with Operator("Translate", {"Frame": ["1", "2"] * 33}, lib=lib) as op:
+        data = b">a\nATGGCCAAATAA\n"
+        assert op.call(data).data == oracle.translate(data, {"Frame": ["1", "2"] * 33})[0]
