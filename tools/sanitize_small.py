@@ -23,6 +23,27 @@ for opts, data in (({"Tabular": True, "All": True}, fq), ({"Tabular": True}, fa)
     with Operator("Stats", opts, device=0) as op:
         op.call(data)
         print("Stats", opts, "ok" if op.stats_render() == oracle.stats(data, opts)[1] else "MISMATCH", flush=True)
+# locate tile kernel (equal-length ACGT panel on wrapped contigs), raw-element operators, the streamed file path
+ctg, _ = synth.native_contigs(512 << 10, seed=9, max_len=200_000)
+ctg = ctg.tobytes()
+lopts = {"Pattern": synth.pattern_panel(200, 12, 40)}
+with Operator("Locate", lopts, device=0) as op:
+    r = op.call(ctg)
+    print("Locate", "ok" if r.data == oracle.locate(ctg, lopts)[0] and op.timings()["fused_blocks"] > 0 else "MISMATCH", flush=True)
+with Operator("Duplicate", {"Times": 3}, device=0) as op:
+    print("Duplicate", "ok" if op.call(fq).data == oracle.duplicate(fq, 3)[0] else "MISMATCH", flush=True)
+with Operator("Range", {"Start": 5, "End": 400}, device=0) as op:
+    print("Range", "ok" if op.call(fa).data == oracle.range_(fa, 5, 400)[0] else "MISMATCH", flush=True)
+import tempfile
+with tempfile.TemporaryDirectory() as td:
+    os.environ["BSK_BLOCK_BYTES"] = "32768"
+    src, dst = os.path.join(td, "in.fq"), os.path.join(td, "out.fq")
+    open(src, "wb").write(fq)
+    with Operator("SeqTransform", {"Reverse": True, "Complement": True}, device=0) as op:
+        op.call_file(src, 0, 0, dst, 0)
+    ok = open(dst, "rb").read() == oracle.seq(fq, {"Reverse": True, "Complement": True})[0]
+    print("bsk_run_file (streamed, 32 KiB blocks)", "ok" if ok else "MISMATCH", flush=True)
+    del os.environ["BSK_BLOCK_BYTES"]
 with Operator("RmDup", {"BySeq": True, "DupSeqsFile": "d", "DupNumFile": "D"}, device=0) as op:
     op.call(fq)
     got = (op.rmdup_dup_seqs(), op.rmdup_dup_num())
