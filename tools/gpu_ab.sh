@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_translate_tile.py tests/test_parity_translate.py -m gpu -x -q 2>&1 | tail -2
-timeout 600 python bench.py --ops-only --ops translate --steps 5 --no-e2e > gpurun_out/r2w_tr.json 2> gpurun_out/r2w_tr.err; python - <<'PY'
+( timeout 400 python bench.py --steps 10 --warmup 3 --ops none 2> gpurun_out/r2x_bench.err ) > gpurun_out/r2x_bench.json; python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2w_tr.json').read().strip().splitlines()[-1])
-for k,v in d['ops'].items(): print(k, round(v['ms_per_step'],3), round(v['roofline']['kernel_ms'],4), round(v['roofline']['frac'],3), v['roofline']['stage_ms'], v['parity']['match'])
+d=json.loads(open('gpurun_out/r2x_bench.json').read().strip().splitlines()[-1])
+print('seq', d['value'], d['ms_per_step'], d['roofline']['frac'], d['config']['l2_policy'][-60:], d['parity']['match'])
 PY
-tail -2 gpurun_out/r2w_tr.err
+tail -2 gpurun_out/r2x_bench.err
+bash tools/gpu_sanitize.sh
