@@ -309,35 +309,78 @@ __global__ void k_contig_check(RecViews v, EmitCfg c, const u8 *__restrict__ kee
   if (!ok) atomicAdd(n_bad, 1ull);
 }
 
+// The CTA's slice of the record table -- output offsets relative to the CTA's first byte, source offsets -- is staged in
+// shared memory first (coalesced loads), so that the per-chunk search and the record walk do not chase global loads;
+// slices of more than kContigCap records (tiny records) read the global arrays as before.
+static const u32 kContigCap = 1024;
 __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__restrict__ off, u8 *__restrict__ out, u64 total,
-                                                     u32 in_bytes) {
+                                                     u32 in_bytes, int stage) {
   __shared__ u32 s_r[2];
+  __shared__ int s_off[kContigCap + 2];   // off[r0 + i] - o0 (negative for a record that starts in front of the CTA)
+  __shared__ u32 s_src[kContigCap + 2];   // first input byte of record r0 + i
   const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
   cta_record_range(off, v.n_rec, o0, total, s_r);
+  const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;  // records r0 .. r0 + nr - 1; entry nr = end of the last one
+  const bool staged = stage && nr <= kContigCap;
+  if (staged) {
+    for (u32 i = threadIdx.x; i <= nr; i += blockDim.x) {
+      const long long rel = (long long)off[r0 + i] - (long long)o0;
+      s_off[i] = rel > 0x7fffffffll ? 0x7fffffff : (rel < -0x7fffffffll ? -0x7fffffff : (int)rel);
+      if (i < nr) s_src[i] = v.name_off[r0 + i] - 1u;
+    }
+    __syncthreads();
+  }
   for (u32 ch = 0; ch < kEmitChunks; ch++) {
     const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
     if (o >= total) return;
-    u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
-    u64 rbeg = off[r], rend = off[r + 1];
     u32 w[4] = {0, 0, 0, 0};
-    u64 pos = o;
     const u64 oend = o + 16 < total ? o + 16 : total;
-    while (pos < oend) {
-      while (pos >= rend) {  // next record with output (dropped ones have no bytes)
-        r++;
-        rbeg = rend;
-        rend = off[r + 1];
+    if (staged) {
+      const int ro = (int)(o - o0), roend = (int)(oend - o0);
+      u32 lo = 0, hi = nr;  // last i with s_off[i] <= ro
+      while (hi - lo > 1) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        if (s_off[mid] <= ro) lo = mid;
+        else hi = mid;
       }
-      // bytes [pos, seg_end) of the chunk come from record r, whose text starts one byte before its name
-      const u64 seg_end = rend < oend ? rend : oend;
-      const u64 src = (u64)(v.name_off[r] - 1u) + (pos - rbeg);
-      const u32 shift = (u32)(pos - o);                 // first chunk byte this record supplies
-      const u32 cnt = (u32)(seg_end - pos);
-      // window aligned to the chunk start; src >= pos >= shift, and bytes in front of the record are masked out
-      u32 ww[4];
-      window16(v.in, src - shift, (u64)in_bytes, ww);
-      merge16(w, ww, shift, cnt);
-      pos = seg_end;
+      u32 i = lo;
+      int rbeg = s_off[i], rend = s_off[i + 1];
+      int pos = ro;
+      while (pos < roend) {
+        while (pos >= rend) {  // next record with output (dropped ones have no bytes)
+          i++;
+          rbeg = rend;
+          rend = s_off[i + 1];
+        }
+        const int seg_end = rend < roend ? rend : roend;
+        const u64 src = (u64)s_src[i] + (u64)(pos - rbeg);
+        const u32 shift = (u32)(pos - ro), cnt = (u32)(seg_end - pos);
+        u32 ww[4];
+        window16(v.in, src - shift, (u64)in_bytes, ww);
+        merge16(w, ww, shift, cnt);
+        pos = seg_end;
+      }
+    } else {
+      u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
+      u64 rbeg = off[r], rend = off[r + 1];
+      u64 pos = o;
+      while (pos < oend) {
+        while (pos >= rend) {  // next record with output (dropped ones have no bytes)
+          r++;
+          rbeg = rend;
+          rend = off[r + 1];
+        }
+        // bytes [pos, seg_end) of the chunk come from record r, whose text starts one byte before its name
+        const u64 seg_end = rend < oend ? rend : oend;
+        const u64 src = (u64)(v.name_off[r] - 1u) + (pos - rbeg);
+        const u32 shift = (u32)(pos - o);                 // first chunk byte this record supplies
+        const u32 cnt = (u32)(seg_end - pos);
+        // window aligned to the chunk start; src >= pos >= shift, and bytes in front of the record are masked out
+        u32 ww[4];
+        window16(v.in, src - shift, (u64)in_bytes, ww);
+        merge16(w, ww, shift, cnt);
+        pos = seg_end;
+      }
     }
     *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -360,7 +403,8 @@ void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes
 void emit_contig(RecViews v, const u64 *out_off, u8 *out, u64 total, u32 in_bytes, cudaStream_t s) {
   if (!total) return;
   const u64 per_cta = 256ull * 16 * kEmitChunks;
-  BSK_LAUNCH(k_emit_contig, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, out_off, out, total, in_bytes);
+  static const int stage = [] { const char *e = getenv("BSK_CONTIG_STAGE"); return e ? atoi(e) : 1; }();  // A/B switch
+  BSK_LAUNCH(k_emit_contig, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, out_off, out, total, in_bytes, stage);
 }
 
 }  // namespace k

@@ -11,7 +11,9 @@
 //   * persistent CTAs (512 threads, 4 per SM) walk 23 KiB tiles with a 1 KiB look-behind, staged by 1-D TMA bulk loads;
 //   * a SWAR newline scan gives every lane its newline masks (-> sequence coordinates) and finds the header lines
 //     (a '>' that follows a newline), whose bytes are overwritten in the stage buffer so that no window spans them;
-//   * every lane rolls the 2-bit code of the last L bases over its 48 bytes (16 bytes of warm-up), skipping newlines;
+//   * every lane packs its 48 bytes (16 bytes of warm-up) into 2-bit codes, a 16-byte chunk at a time (SWAR: code =
+//     bits 1-2 of the letter, validity by rebuilding the letter from the code; a single newline is cut out of the
+//     packed word), keeps the codes of the last 16 bases beside and takes every window with one funnel shift;
 //     each window probes a two-hash Bloom bitmap of the needle codes in shared memory (patterns and, for the '-'
 //     strand, reverse(pair(pattern)) -- matched on the forward strand, bigseqkit-lib/locate.go:669-766); the rare
 //     positives are parked in a shared-memory queue and confirmed by the whole CTA in an exact table in L2;
@@ -63,6 +65,21 @@ __device__ __forceinline__ u32 lt_nl_flags(u32 w) {
   return ~(y | x) & 0x80808080u;
 }
 
+// Bloom probe: bit (h >> (32 - FBITS)) of the bitmap, stored from the top of each word (bit 31 - (index & 31)) so that
+// a wrapping left shift by the index puts it into the sign bit; the bitmap sits on a 16 KiB boundary of shared memory,
+// which lets the word address be formed with one AND-OR.
+__device__ __forceinline__ bool lt_probe(const u32 *filt, u32 fbase, u32 h) {
+#ifdef BSK_EMU
+  (void)fbase;
+  const u32 w = filt[h >> (37u - lt::FBITS)];
+#else
+  (void)filt;
+  u32 w;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(((h >> (35u - lt::FBITS)) & (4u * lt::FWORDS - 4u)) | fbase));
+#endif
+  return (int)__funnelshift_l(0u, w, h >> (32u - lt::FBITS)) < 0;
+}
+
 // exact confirmation of a candidate window (code `key`, last base at global byte gend) against the needle table
 __device__ __forceinline__ void lt_confirm(const LocateTileArgs &a, u32 key, u32 gend, u32 nl, u32 tile) {
   u32 slot = (key * 0x9E3779B1u) >> a.tshift;
@@ -87,7 +104,7 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
   using namespace lt;
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
-  __align__(16) __shared__ u32 s_filter[FWORDS];
+  __align__(4 * FWORDS) __shared__ u32 s_filter[FWORDS];
   __align__(16) __shared__ u8 s_lut[256];
   __shared__ u32 s_wtot[NWARP];
   __shared__ u32 s_decline, s_nl_lb, s_qn;
@@ -95,6 +112,12 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
   const u32 n = a.n, n16 = n & ~15u;
   const u32 L = a.L;
 
+#ifdef BSK_EMU
+  const u32 fbase = 0;
+#else
+  const u32 fbase = (u32)__cvta_generic_to_shared(s_filter);
+  if (fbase & (4u * FWORDS - 1u)) __trap();  // lt_probe relies on the alignment
+#endif
   if (tid < 256) s_lut[tid] = a.lut[tid];
   for (u32 i = tid; i < FWORDS; i += NT) s_filter[i] = a.filter[i];
   if (tid == 0) {
@@ -224,60 +247,134 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
     }
     __syncthreads();
 
-    // ---- rolling 2-bit code over the lane's span (owned lanes only).  Every complete window probes the Bloom bitmap;
-    // the few that pass both probes are parked in the queue and confirmed after the loop.
+    // ---- 2-bit codes of the lane's span, one 16-byte chunk at a time (owned lanes only).  A chunk of 16 plain bases,
+    // or of 15 and one newline, is packed with SWAR arithmetic (first base in the highest bits) and appended to the
+    // codes of the 16 bases before it; every window is then one funnel shift away.  Each window probes the Bloom
+    // bitmap; the few that pass both probes are parked in the queue and confirmed after the loop.  Any other chunk
+    // (invalid bases, header bytes, several newlines) goes byte by byte through the class table.
+    const u32 prev_m2 = __shfl_up_sync(0xffffffffu, m[2], 1);  // newline flags of the 16 bytes in front of the span
     if (tid >= LBL && span0 < lim) {
-      u32 code = 0, run = 0, nb = 0, brk = 0;
-      {  // warm-up: the WU bytes in front of the span
-        const uint4 *vp = reinterpret_cast<const uint4 *>(d + span0 - WU);
-#pragma unroll
-        for (u32 v = 0; v < WU / 16; v++) {
-          const uint4 q = vp[v];
-          const u32 w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (u32 j = 0; j < 16; j++) {
-            const u32 c = s_lut[__byte_perm(w4[j >> 2], 0u, 0x4440u + (j & 3u))];
-            if (c & C_BASE) { code = code * 4u + (c & 3u); run++; }
+      u32 code = 0, run = 0;  // codes of the last 16 bases, length of the run of valid bases behind them (saturating)
+      const u32 vmask = a.vmask, vbase = a.vbase;
+      // hit: window whose last base is byte `rel` of the span
+      auto park = [&](u32 c, u32 rel) {
+        const u32 p = span0 + rel;  // region position of the window's last base
+        if (p >= lim) return;
+        u32 nls = 0;  // newlines of the span in front of p
+        if (rel >= 32u) nls += (u32)__popc(m[0]);
+        if (rel >= 64u) nls += (u32)__popc(m[1]);
+        const u32 mk = rel < 32u ? m[0] : (rel < 64u ? m[1] : m[2]);
+        nls += (u32)__popc(mk & ((1u << (rel & 31u)) - 1u));
+        const u32 qi = atomicAdd(&s_qn, 1u);
+        const u32 key = c & a.cmask, gend = t0 + (p - LB), nl = nl_before - nl_lookbehind + nls;
+        if (qi < QCAP) { sm.qkey[qi] = key; sm.qpos[qi] = gend; sm.qnl[qi] = nl; }
+        else lt_confirm(a, key, gend, nl, tile);  // queue full (a panel that matches everywhere): confirm in place
+      };
+      // byte-wise path over one chunk at offset rel0 of the span (the warm-up does not probe)
+      auto bytewise = [&](const uint4 &q, u32 rel0, bool probe, u32 &nb, u32 &brk) {
+#pragma unroll 1
+        for (u32 i = 0; i < 4; i++) {
+          const u32 w = i == 0 ? q.x : (i == 1 ? q.y : (i == 2 ? q.z : q.w));
+#pragma unroll 1
+          for (u32 j = 0; j < 4; j++) {
+            const u32 c = s_lut[(w >> (8u * j)) & 0xffu];
+            if (c & C_BASE) {
+              code = code * 4u + (c & 3u);
+              run++;
+              if (probe) {
+                const u32 h1 = code * kmul;  // depends on the last L bases only (kmul = odd << (32 - 2L))
+                if (lt_probe(s_filter, fbase, h1) && lt_probe(s_filter, fbase, code * kmul2) && run >= L) park(code, rel0 + 4u * i + j);
+              }
+            }
             if (c & C_RESET) run = 0;
             nb += (c >> 4) & 1u;
             brk |= c;
           }
         }
-        // too few symbols in the warm-up to judge the first windows of the span (a run of > 16 newlines)
-        if (nb + 1u < L && !(brk & C_BREAK) && t0 + span0 >= LB + WU) s_decline = 1;
+      };
+      // packs the chunk; true when it is 16 bases (cnt = 16) or 15 bases and the newline at byte k (cnt = 15)
+      auto pack = [&](const uint4 &q, u32 nl16, u32 &lo, u32 &hi, u32 &cnt, u32 &k) {
+        const u32 one = (nl16 != 0u && (nl16 & (nl16 - 1u)) == 0u) ? 1u : 0u;
+        k = nl16 ? (u32)__ffs((int)nl16) - 1u : 16u;
+        // a single newline is turned into the first base letter before the test and its (zero) code removed afterwards
+        const u32 fix = one ? ((0x0au ^ (vbase & 0xffu)) << (8u * (k & 3u))) : 0u;
+        const u32 kw = one ? (k >> 2) : 4u;
+        u32 w4[4] = {q.x, q.y, q.z, q.w};
+        u32 bad = 0, p = 0;
+#pragma unroll
+        for (u32 i = 0; i < 4; i++) {
+          const u32 wm = (w4[i] ^ (kw == i ? fix : 0u)) & vmask;
+          const u32 x = (wm >> 1) & 0x03030303u;                 // A 0, C 1, T 2, G 3 (either case)
+          const u32 t = (x >> 1) & ~x & 0x01010101u;             // the T bytes
+          const u32 expect = x * 2u + vbase + t * 0x0fu;         // the letter each code stands for: 41 43 47, 54 = 45 + 0f
+          bad |= wm ^ expect;
+          p = (p << 8) | ((x * 0x40100401u) >> 24);              // four codes -> one byte, first base highest
+        }
+        if (bad != 0u || (nl16 != 0u && !one)) return false;
+        if (one) {
+          const u32 below = 0x3fffffffu >> (2u * k);             // the codes behind the newline
+          const u32 p30 = ((p & ~(0xffffffffu >> (2u * k))) >> 2) | (p & below);
+          lo = (code << 30) | p30;
+          hi = code >> 2;
+          cnt = 15u;
+        } else {
+          lo = p;
+          hi = code;
+          cnt = 16u;
+        }
+        return true;
+      };
+      {  // warm-up: the WU bytes in front of the span (no probes)
+        const uint4 q = *reinterpret_cast<const uint4 *>(d + span0 - WU);
+        u32 nlw;
+        if (lane != 0u) nlw = prev_m2 >> 16;
+        else {
+          u32 lo2 = __dp4a(lt_nl_flags(q.x), 0x08040201u, 0u);
+          lo2 = __dp4a(lt_nl_flags(q.y), 0x80402010u, lo2);
+          u32 hi2 = __dp4a(lt_nl_flags(q.z), 0x08040201u, 0u);
+          hi2 = __dp4a(lt_nl_flags(q.w), 0x80402010u, hi2);
+          nlw = (lo2 >> 7) | (hi2 << 1);
+        }
+        u32 lo, hi, cnt, k;
+        if (pack(q, nlw, lo, hi, cnt, k)) {
+          code = lo;
+          run = cnt;
+        } else {
+          u32 nb = 0, brk = 0;
+          bytewise(q, 0u, false, nb, brk);
+          // too few symbols in the warm-up to judge the first windows of the span (a run of > 16 newlines)
+          if (nb + 1u < L && !(brk & C_BREAK) && t0 + span0 >= LB + WU) s_decline = 1;
+        }
       }
       const uint4 *vp = reinterpret_cast<const uint4 *>(d + span0);
 #pragma unroll 1
       for (u32 v = 0; v < NCH; v++) {
         const uint4 q = vp[v];
-        const u32 w4[4] = {q.x, q.y, q.z, q.w};
+        const u32 mw = (v >> 1) == 0u ? m[0] : ((v >> 1) == 1u ? m[1] : m[2]);
+        const u32 nl16 = (v & 1u) ? (mw >> 16) : (mw & 0xffffu);
+        u32 lo, hi, cnt, k;
+        if (pack(q, nl16, lo, hi, cnt, k)) {
+          const u32 need = L > run ? L - run : 0u;  // windows whose last base is base >= need - 1 of the chunk are whole
+          u32 hm = 0;                               // windows that pass both probes (bit i)
 #pragma unroll
-        for (u32 j = 0; j < 16; j++) {
-          const u32 c = s_lut[__byte_perm(w4[j >> 2], 0u, 0x4440u + (j & 3u))];
-          if (c & C_BASE) {
-            code = code * 4u + (c & 3u);
-            run++;
-            const u32 h1 = code * kmul;  // depends on the last L bases only (kmul = odd << (32 - 2L))
-            if ((s_filter[h1 >> (37u - FBITS)] >> ((h1 >> (32u - FBITS)) & 31u)) & 1u) {
-              const u32 h2 = code * kmul2;
-              if (((s_filter[h2 >> (37u - FBITS)] >> ((h2 >> (32u - FBITS)) & 31u)) & 1u) && run >= L) {
-                const u32 p = span0 + v * 16u + j;  // region position of the window's last base
-                if (p < lim) {
-                  const u32 rel = p - span0;
-                  u32 nls = 0;  // newlines of the span in front of p
-                  if (rel >= 32u) nls += (u32)__popc(m[0]);
-                  if (rel >= 64u) nls += (u32)__popc(m[1]);
-                  const u32 mk = rel < 32u ? m[0] : (rel < 64u ? m[1] : m[2]);
-                  nls += (u32)__popc(mk & ((1u << (rel & 31u)) - 1u));
-                  const u32 qi = atomicAdd(&s_qn, 1u);
-                  const u32 key = code & a.cmask, gend = t0 + (p - LB), nl = nl_before - nl_lookbehind + nls;
-                  if (qi < QCAP) { sm.qkey[qi] = key; sm.qpos[qi] = gend; sm.qnl[qi] = nl; }
-                  else lt_confirm(a, key, gend, nl, tile);  // queue full (a panel that matches everywhere): confirm in place
-                }
-              }
-            }
+          for (u32 i = 0; i < 16; i++) {            // i = bases of the chunk behind the window's last one
+            const u32 c = __funnelshift_r(lo, hi, 2u * i);
+            const u32 h1 = c * kmul;
+            if (lt_probe(s_filter, fbase, h1) && lt_probe(s_filter, fbase, c * kmul2)) hm |= 1u << i;
           }
-          if (c & C_RESET) run = 0;
+          if (cnt != 16u) hm &= 0x7fffu;            // 15 bases: the window 15 bases back ended in the previous chunk
+          while (hm) {                              // rare
+            const u32 i = 31u - (u32)__clz((int)hm);  // earliest window first
+            hm ^= 1u << i;
+            const u32 jb = cnt - 1u - i;            // index of the window's last base among the chunk's bases
+            if (jb + 1u >= need) park(__funnelshift_r(lo, hi, 2u * i), v * 16u + jb + (jb >= k ? 1u : 0u));
+          }
+          code = lo;
+          run = run + cnt;
+          if (run > 64u) run = 64u;
+        } else {
+          u32 nb = 0, brk = 0;
+          bytewise(q, v * 16u, true, nb, brk);
         }
       }
     }

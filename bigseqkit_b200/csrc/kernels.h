@@ -128,6 +128,7 @@ struct LocateTileArgs {
   const u32 *filter;    // Bloom bitmap of the needle codes, locate_tile_filter_bits() bits (copied to shared memory)
   u32 kmul, kmul2;      // bit index i = (code * kmul_i) >> (32 - bits); kmul_i = odd << (32 - 2L)
   u32 L, cmask;         // pattern length, mask of the 2L code bits
+  u32 vmask, vbase;     // letters of the panel's case: (byte & vmask) must be one of vbase + {0, 2, 6, 0x13} in every byte
   const u32 *table;     // exact table: pairs {code, first needle + 1 (0 = empty)}, open addressing
   u32 tmask, tshift;
   const u32 *nd_code, *nd_ps;  // needles sorted by code: code, pattern << 1 | strand

@@ -533,7 +533,7 @@ int Engine::build_kmer_tables() {
     if (upper || o_.IgnoreCase) lut[(u8)up] = (u8)(8 | 16 | code);
     if (lower || o_.IgnoreCase) lut[(u8)(up + 32)] = (u8)(8 | 16 | code);
   };
-  base('A', 0); base('C', 1); base('G', 2); base('T', 3);
+  base('A', 0); base('C', 1); base('T', 2); base('G', 3);  // bits 1-2 of the letter, as the kernel's SWAR path packs them
   const u32 cmask = L == 16 ? 0xffffffffu : ((1u << (2 * L)) - 1u);
   struct Nd { u32 code, ps; };
   std::vector<Nd> nd;
@@ -555,8 +555,8 @@ int Engine::build_kmer_tables() {
     codes.push_back(nd[i].code);
     pss.push_back(nd[i].ps);
     const u32 bi = (nd[i].code * kmul) >> (32 - fbits), bi2 = (nd[i].code * kmul2) >> (32 - fbits);
-    filter[bi >> 5] |= 1u << (bi & 31);
-    filter[bi2 >> 5] |= 1u << (bi2 & 31);
+    filter[bi >> 5] |= 0x80000000u >> (bi & 31);  // from the top of the word: lt_probe shifts the bit into the sign
+    filter[bi2 >> 5] |= 0x80000000u >> (bi2 & 31);
     if (i > 0 && nd[i - 1].code == nd[i].code) continue;  // the table points at the first needle of a code run
     u32 slot = (nd[i].code * 0x9E3779B1u) >> tshift;
     while (table[2 * slot + 1]) slot = (slot + 1) & (tsize - 1);
@@ -565,6 +565,8 @@ int Engine::build_kmer_tables() {
   }
   ps.kL = (u32)L; ps.kfbits = fbits; ps.kmul = kmul; ps.kmul2 = kmul2; ps.kcmask = cmask; ps.ktmask = tsize - 1; ps.ktshift = tshift;
   ps.kn = (u32)nd.size();
+  ps.kvmask = o_.IgnoreCase ? 0xdfdfdfdfu : 0xffffffffu;
+  ps.kvbase = (lower && !o_.IgnoreCase) ? 0x61616161u : 0x41414141u;
   upload(ps.klut, lut, stream);
   upload(ps.kfilter, filter, stream);
   upload(ps.ktable, table, stream);
@@ -615,6 +617,8 @@ int Engine::op_locate_tile(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
   a.kmul2 = ps.kmul2;
   a.L = ps.kL;
   a.cmask = ps.kcmask;
+  a.vmask = ps.kvmask;
+  a.vbase = ps.kvbase;
   a.table = ps.ktable.as<u32>();
   a.tmask = ps.ktmask;
   a.tshift = ps.ktshift;
