@@ -14,9 +14,11 @@
 //   * every lane packs its 48 bytes (16 bytes of warm-up) into 2-bit codes, a 16-byte chunk at a time (SWAR: code =
 //     bits 1-2 of the letter, validity by rebuilding the letter from the code; a single newline is cut out of the
 //     packed word), keeps the codes of the last 16 bases beside and takes every window with one funnel shift;
-//     each window probes a two-hash Bloom bitmap of the needle codes in shared memory (patterns and, for the '-'
-//     strand, reverse(pair(pattern)) -- matched on the forward strand, bigseqkit-lib/locate.go:669-766); the rare
-//     positives are parked in a shared-memory queue and confirmed by the whole CTA in an exact table in L2;
+//     each window probes a bitmap of the needle codes in shared memory (patterns and, for the '-' strand,
+//     reverse(pair(pattern)) -- matched on the forward strand, bigseqkit-lib/locate.go:669-766) without a branch: the
+//     16 result bits of a chunk are collected in a mask, and the few set ones (3 % of the windows with 2000 codes) look
+//     their 16-bit fingerprint up in a second table; what passes both is parked in a shared-memory queue and confirmed
+//     by the whole CTA in an exact table in L2;
 //   * header positions and per-tile newline counts are written beside, from which a small second kernel derives the
 //     record table (ID slice, sequence length) and turns raw hit positions into (record, 0-based start).
 // HBM traffic = N read (+ 4 % look-behind re-read, served by L2) for N algorithmic bytes.
@@ -41,7 +43,8 @@ constexpr u32 HDR_MAX = 960;             // longest header line accepted (must s
 constexpr u32 NWARP = NT / 32;
 constexpr u32 FBITS = 17;                // Bloom bitmap: 2^17 bits = 16 KiB, two probes per window
 constexpr u32 FWORDS = (1u << FBITS) / 32;
-constexpr u32 QCAP = 1024;               // candidates per tile parked for the confirmation pass
+constexpr u32 PBITS = 12;                // fingerprint table: 2^12 x 16 bits = 8 KiB
+constexpr u32 QCAP = 256;                // candidates per tile parked for the confirmation pass
 constexpr u32 CTAS = 4;                  // CTAs per SM: one stage buffer each, the other CTAs hide the load
 static_assert(T % 16 == 0 && LB % 16 == 0 && SPAN % 16 == 0 && WU % 16 == 0 && HDR_MAX + WU < LB && LBL < 32 && (NCH == 3 || NCH == 6),
               "tile geometry");
@@ -65,19 +68,22 @@ __device__ __forceinline__ u32 lt_nl_flags(u32 w) {
   return ~(y | x) & 0x80808080u;
 }
 
-// Bloom probe: bit (h >> (32 - FBITS)) of the bitmap, stored from the top of each word (bit 31 - (index & 31)) so that
-// a wrapping left shift by the index puts it into the sign bit; the bitmap sits on a 16 KiB boundary of shared memory,
-// which lets the word address be formed with one AND-OR.
-__device__ __forceinline__ bool lt_probe(const u32 *filt, u32 fbase, u32 h) {
-#ifdef BSK_EMU
-  (void)fbase;
-  const u32 w = filt[h >> (37u - lt::FBITS)];
-#else
-  (void)filt;
-  u32 w;
-  asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(((h >> (35u - lt::FBITS)) & (4u * lt::FWORDS - 4u)) | fbase));
-#endif
-  return (int)__funnelshift_l(0u, w, h >> (32u - lt::FBITS)) < 0;
+// First level: one bit of a 2^FBITS-bit map per needle code, stored from the top of each word (bit 31 - (index & 31)) so
+// that a wrapping left shift by the index puts it into the sign bit of the result.
+__device__ __forceinline__ u32 lt_probe(const u32 *filt, u32 h) {
+  return __funnelshift_l(0u, filt[h >> (37u - lt::FBITS)], h >> (32u - lt::FBITS));
+}
+// Second level: open-addressing table of 16-bit fingerprints (0 = empty slot) under a second hash of the code; a window
+// that finds its fingerprint is almost surely a needle and goes to the exact table.
+__device__ __forceinline__ bool lt_probe2(const unsigned short *fp, u32 h2) {
+  u32 slot = h2 >> (32u - lt::PBITS);
+  const u32 want = ((h2 >> 5) & 0x7fffu) | 0x8000u;
+  for (;;) {
+    const u32 e = fp[slot];
+    if (e == want) return true;
+    if (e == 0u) return false;
+    slot = (slot + 1u) & ((1u << lt::PBITS) - 1u);
+  }
 }
 
 // exact confirmation of a candidate window (code `key`, last base at global byte gend) against the needle table
@@ -104,7 +110,8 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
   using namespace lt;
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
-  __align__(4 * FWORDS) __shared__ u32 s_filter[FWORDS];
+  __align__(16) __shared__ u32 s_filter[FWORDS];
+  __align__(16) __shared__ unsigned short s_fp[1u << PBITS];
   __align__(16) __shared__ u8 s_lut[256];
   __shared__ u32 s_wtot[NWARP];
   __shared__ u32 s_decline, s_nl_lb, s_qn;
@@ -112,14 +119,9 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
   const u32 n = a.n, n16 = n & ~15u;
   const u32 L = a.L;
 
-#ifdef BSK_EMU
-  const u32 fbase = 0;
-#else
-  const u32 fbase = (u32)__cvta_generic_to_shared(s_filter);
-  if (fbase & (4u * FWORDS - 1u)) __trap();  // lt_probe relies on the alignment
-#endif
   if (tid < 256) s_lut[tid] = a.lut[tid];
   for (u32 i = tid; i < FWORDS; i += NT) s_filter[i] = a.filter[i];
+  for (u32 i = tid; i < (1u << PBITS) / 2; i += NT) reinterpret_cast<u32 *>(s_fp)[i] = reinterpret_cast<const u32 *>(a.fptab)[i];
   if (tid == 0) {
     tma::mbar_init(&sm.full, 1);
     tma::fence_barrier_init();
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
     // codes of the 16 bases before it; every window is then one funnel shift away.  Each window probes the Bloom
     // bitmap; the few that pass both probes are parked in the queue and confirmed after the loop.  Any other chunk
     // (invalid bases, header bytes, several newlines) goes byte by byte through the class table.
-    const u32 prev_m2 = __shfl_up_sync(0xffffffffu, m[2], 1);  // newline flags of the 16 bytes in front of the span
+    // newline flags of the 16 bytes in front of the span = of the previous lane's last chunk
+    const u32 prev_m2 = __shfl_up_sync(0xffffffffu, NCH == 3 ? (m[1] << 16) : m[2], 1);
     if (tid >= LBL && span0 < lim) {
       u32 code = 0, run = 0;  // codes of the last 16 bases, length of the run of valid bases behind them (saturating)
       const u32 vmask = a.vmask, vbase = a.vbase;
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
               run++;
               if (probe) {
                 const u32 h1 = code * kmul;  // depends on the last L bases only (kmul = odd << (32 - 2L))
-                if (lt_probe(s_filter, fbase, h1) && lt_probe(s_filter, fbase, code * kmul2) && run >= L) park(code, rel0 + 4u * i + j);
+                if ((int)lt_probe(s_filter, h1) < 0 && run >= L && lt_probe2(s_fp, code * kmul2)) park(code, rel0 + 4u * i + j);
               }
             }
             if (c & C_RESET) run = 0;
@@ -355,19 +358,19 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
         u32 lo, hi, cnt, k;
         if (pack(q, nl16, lo, hi, cnt, k)) {
           const u32 need = L > run ? L - run : 0u;  // windows whose last base is base >= need - 1 of the chunk are whole
-          u32 hm = 0;                               // windows that pass both probes (bit i)
+          u32 hm = 0;                               // windows that pass the first probe (bit 15 - i)
 #pragma unroll
           for (u32 i = 0; i < 16; i++) {            // i = bases of the chunk behind the window's last one
             const u32 c = __funnelshift_r(lo, hi, 2u * i);
-            const u32 h1 = c * kmul;
-            if (lt_probe(s_filter, fbase, h1) && lt_probe(s_filter, fbase, c * kmul2)) hm |= 1u << i;
+            hm = __funnelshift_l(lt_probe(s_filter, c * kmul), hm, 1u);  // the sign bit enters from below
           }
-          if (cnt != 16u) hm &= 0x7fffu;            // 15 bases: the window 15 bases back ended in the previous chunk
-          while (hm) {                              // rare
-            const u32 i = 31u - (u32)__clz((int)hm);  // earliest window first
-            hm ^= 1u << i;
+          if (cnt != 16u) hm &= ~1u;                // 15 bases: the window 15 bases back ended in the previous chunk
+          while (hm) {                              // a few per warp and chunk
+            const u32 i = 16u - (u32)__ffs((int)hm);
+            hm &= hm - 1u;
+            const u32 c = __funnelshift_r(lo, hi, 2u * i);
             const u32 jb = cnt - 1u - i;            // index of the window's last base among the chunk's bases
-            if (jb + 1u >= need) park(__funnelshift_r(lo, hi, 2u * i), v * 16u + jb + (jb >= k ? 1u : 0u));
+            if (jb + 1u >= need && lt_probe2(s_fp, c * kmul2)) park(c, v * 16u + jb + (jb >= k ? 1u : 0u));
           }
           code = lo;
           run = run + cnt;
@@ -444,6 +447,7 @@ __global__ void k_locate_resolve(u64 *hitA, u64 *hitB, u64 n_hits, const u64 *__
 u32 locate_tile_tiles(u32 n) { return (n + lt::T - 1) / lt::T; }
 u32 locate_tile_bytes() { return lt::T; }
 u32 locate_tile_filter_bits() { return lt::FBITS; }
+u32 locate_tile_fp_bits() { return lt::PBITS; }
 
 void locate_tile(LocateTileArgs a, int n_sm, cudaStream_t s) {
   a.n_tiles = locate_tile_tiles(a.n);

@@ -126,6 +126,7 @@ struct LocateTileArgs {
   u32 n, n_tiles;
   const u8 *lut;        // 256 byte classes (lt::C_*)
   const u32 *filter;    // Bloom bitmap of the needle codes, locate_tile_filter_bits() bits (copied to shared memory)
+  const unsigned short *fptab;  // fingerprint table, 2^locate_tile_fp_bits() entries (copied to shared memory)
   u32 kmul, kmul2;      // bit index i = (code * kmul_i) >> (32 - bits); kmul_i = odd << (32 - 2L)
   u32 L, cmask;         // pattern length, mask of the 2L code bits
   u32 vmask, vbase;     // letters of the panel's case: (byte & vmask) must be one of vbase + {0, 2, 6, 0x13} in every byte
@@ -143,6 +144,7 @@ struct LocateTileArgs {
 u32 locate_tile_tiles(u32 n);
 u32 locate_tile_bytes();
 u32 locate_tile_filter_bits();
+u32 locate_tile_fp_bits();
 void locate_tile(LocateTileArgs a, int n_sm, cudaStream_t s);
 void locate_records(const u8 *in, u32 n, const u64 *hdr_off, const u64 *hdr_nl, const u32 *tile_nl_base, u32 n_tiles, u32 n_rec,
                     u32 *name_off, u32 *name_len, u32 *seq_start, u32 *seq_nl, u32 *seq_len, cudaStream_t s);

@@ -57,7 +57,7 @@ struct Engine::PatternSet {
   std::vector<u32> needle_ps;
   bool kmer_built = false, kmer_ok = false;
   u32 kL = 0, kfbits = 0, kmul = 0, kmul2 = 0, kcmask = 0, ktmask = 0, ktshift = 0, kn = 0, kvmask = 0, kvbase = 0;
-  DevBuf klut, kfilter, ktable, kcode, kps;
+  DevBuf klut, kfilter, kfptab, ktable, kcode, kps;
 };
 
 void rmdup_state_free(Engine::RmdupState *rm);

@@ -546,6 +546,9 @@ int Engine::build_kmer_tables() {
   const u32 fbits = k::locate_tile_filter_bits();
   const u32 kmul = 0x9E3779B1u << (32 - 2 * L), kmul2 = 0x85EBCA6Bu << (32 - 2 * L);
   std::vector<u32> filter((1u << fbits) / 32, 0);
+  const u32 pbits = k::locate_tile_fp_bits();
+  if (nd.size() * 2 > (1u << pbits)) return BSK_OK;  // the fingerprint table would be too full: general path
+  std::vector<unsigned short> fptab(1u << pbits, 0);
   u32 tsize = 16;
   while (tsize < nd.size() * 4) tsize *= 2;
   u32 tshift = 32;
@@ -554,9 +557,14 @@ int Engine::build_kmer_tables() {
   for (size_t i = 0; i < nd.size(); i++) {
     codes.push_back(nd[i].code);
     pss.push_back(nd[i].ps);
-    const u32 bi = (nd[i].code * kmul) >> (32 - fbits), bi2 = (nd[i].code * kmul2) >> (32 - fbits);
+    const u32 bi = (nd[i].code * kmul) >> (32 - fbits);
     filter[bi >> 5] |= 0x80000000u >> (bi & 31);  // from the top of the word: lt_probe shifts the bit into the sign
-    filter[bi2 >> 5] |= 0x80000000u >> (bi2 & 31);
+    {  // second level: 16-bit fingerprint under the second hash, linear probing (k_locate_tile.cu lt_probe2)
+      const u32 h2 = nd[i].code * kmul2, want = ((h2 >> 5) & 0x7fffu) | 0x8000u;
+      u32 slot = h2 >> (32 - pbits);
+      while (fptab[slot] && fptab[slot] != want) slot = (slot + 1) & ((1u << pbits) - 1);
+      fptab[slot] = (unsigned short)want;
+    }
     if (i > 0 && nd[i - 1].code == nd[i].code) continue;  // the table points at the first needle of a code run
     u32 slot = (nd[i].code * 0x9E3779B1u) >> tshift;
     while (table[2 * slot + 1]) slot = (slot + 1) & (tsize - 1);
@@ -569,6 +577,7 @@ int Engine::build_kmer_tables() {
   ps.kvbase = (lower && !o_.IgnoreCase) ? 0x61616161u : 0x41414141u;
   upload(ps.klut, lut, stream);
   upload(ps.kfilter, filter, stream);
+  upload(ps.kfptab, fptab, stream);
   upload(ps.ktable, table, stream);
   upload(ps.kcode, codes, stream);
   upload(ps.kps, pss, stream);
@@ -613,6 +622,7 @@ int Engine::op_locate_tile(const u8 *d_in, u32 n, int64_t pid, BlockOut &bo) {
   a.n = n;
   a.lut = ps.klut.as<u8>();
   a.filter = ps.kfilter.as<u32>();
+  a.fptab = ps.kfptab.as<unsigned short>();
   a.kmul = ps.kmul;
   a.kmul2 = ps.kmul2;
   a.L = ps.kL;
