@@ -323,7 +323,10 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
   __shared__ u32 s_src[kContigCap + 2];   // first input byte of record r0 + i
   __shared__ u32 s_map[NCHUNK];           // chunk -> last record with output that starts at or before the chunk
   __shared__ u32 s_wmax[8];
+  __shared__ unsigned short s_slow[NCHUNK];  // chunks that are not one plain window
+  __shared__ u32 s_nslow;
   const u32 tid = threadIdx.x;
+  if (tid == 0) s_nslow = 0;
   const u64 o0 = (u64)blockIdx.x * NCHUNK * 16ull;
   cta_record_range(off, v.n_rec, o0, total, s_r);
   const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;  // records r0 .. r0 + nr - 1; entry nr = end of the last one
@@ -401,36 +404,46 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
         }
       }
     }
-    // phase 2: shift and store; the other chunks (record boundaries, the ragged end) take the general walk
+    // phase 2: shift and store.  The other chunks (record boundaries: one or two lanes of every warp, and the ragged
+    // end) are put on a list and done afterwards by as many threads side by side -- inside this loop every warp would
+    // run the general walk for its one lane.
 #pragma unroll
     for (u32 ch = 0; ch < kEmitChunks; ch++) {
       const u32 cidx = ch * 256u + tid;
       const u64 o = o0 + (u64)cidx * 16ull;
-      if (o >= total) break;
-      u32 w[4] = {0, 0, 0, 0};
       if (fast[ch]) {
+        u32 w[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) w[q] = __funnelshift_r(ld[ch][q], ld[ch][q + 1], sh[ch]);
-      } else {
-        const u64 oend = o + 16 < total ? o + 16 : total;
-        const int ro = (int)(cidx * 16u), roend = (int)(oend - o0);
-        u32 i = s_map[cidx];
-        int rbeg = s_off[i], rend = s_off[i + 1];
-        int pos = ro;
-        while (pos < roend) {
-          while (pos >= rend) {  // next record with output (dropped ones have no bytes)
-            i++;
-            rbeg = rend;
-            rend = s_off[i + 1];
-          }
-          const int seg_end = rend < roend ? rend : roend;
-          const u64 src = (u64)s_src[i] + (u64)(pos - rbeg);
-          const u32 shift = (u32)(pos - ro), cnt = (u32)(seg_end - pos);
-          u32 ww[4];
-          window16(v.in, src - shift, (u64)in_bytes, ww);
-          merge16(w, ww, shift, cnt);
-          pos = seg_end;
+        *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else if (o < total) {
+        s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)cidx;
+      }
+    }
+    __syncthreads();
+    const u32 nslow = s_nslow;
+    for (u32 t = tid; t < nslow; t += 256) {
+      const u32 cidx = s_slow[t];
+      const u64 o = o0 + (u64)cidx * 16ull;
+      u32 w[4] = {0, 0, 0, 0};
+      const u64 oend = o + 16 < total ? o + 16 : total;
+      const int ro = (int)(cidx * 16u), roend = (int)(oend - o0);
+      u32 i = s_map[cidx];
+      int rbeg = s_off[i], rend = s_off[i + 1];
+      int pos = ro;
+      while (pos < roend) {
+        while (pos >= rend) {  // next record with output (dropped ones have no bytes)
+          i++;
+          rbeg = rend;
+          rend = s_off[i + 1];
         }
+        const int seg_end = rend < roend ? rend : roend;
+        const u64 src = (u64)s_src[i] + (u64)(pos - rbeg);
+        const u32 shift = (u32)(pos - ro), cnt = (u32)(seg_end - pos);
+        u32 ww[4];
+        window16(v.in, src - shift, (u64)in_bytes, ww);
+        merge16(w, ww, shift, cnt);
+        pos = seg_end;
       }
       *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
     }

@@ -1,23 +1,23 @@
 #!/bin/bash
 # check C: two-level locate probe + map-based k_emit_contig
 OUT=gpurun_out; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_locate_tile.py tests/test_parity_match.py tests/test_parity_rmdup.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -3
-( timeout 600 python bench.py --ops-only --ops locate,rmdup --steps 10 --no-e2e --no-cpu-baseline 2> $OUT/r3c_bench.err ) > $OUT/r3c_bench.json
-tail -1 $OUT/r3c_bench.err
+timeout 900 python -m pytest tests/test_locate_tile.py tests/test_parity_match.py tests/test_parity_rmdup.py -m gpu -x -q 2>&1 | tail -3
+( timeout 600 python bench.py --ops-only --ops locate,rmdup --steps 10 --no-e2e --no-cpu-baseline 2> $OUT/r3d_bench.err ) > $OUT/r3d_bench.json
+tail -1 $OUT/r3d_bench.err
 for wl in rmdup locate; do
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/r3c_launches_$wl.csv \
-  python bench.py --ops-only --ops $wl --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3c_ncu_$wl.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/r3d_launches_$wl.csv \
+  python bench.py --ops-only --ops $wl --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3d_ncu_$wl.log 2>&1
 done
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_locate_tile -s 3 -c 1 -f -o $OUT/r3c_locate_prof \
-  python bench.py --ops-only --ops locate --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3c_ncu_locate.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_locate_tile -s 3 -c 1 -f -o $OUT/r3d_locate_prof \
+  python bench.py --ops-only --ops locate --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3d_ncu_locate.log 2>&1
 python - <<'PY'
 import json,csv,collections
-for f in ('r3c_bench.json',):
+for f in ('r3d_bench.json',):
     try:
         d=json.loads(open('gpurun_out/'+f).read().strip().splitlines()[-1])
         for k,v in d['ops'].items(): print(f,k,'ms',round(v['ms_per_step'],4),'kernel_ms',round(v['roofline']['kernel_ms'],4),'frac',round(v['roofline']['frac'],4),v.get('parity',{}).get('match'))
     except Exception as e: print(f,'ERR',e)
-for f in ('r3c_launches_rmdup.csv','r3c_launches_locate.csv'):
+for f in ('r3d_launches_rmdup.csv','r3d_launches_locate.csv'):
     try:
         rows=[r for r in csv.reader(l for l in open('gpurun_out/'+f) if l.startswith('"'))]
         h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
