@@ -218,73 +218,222 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
   return pc;
 }
 
-// One aligned 16-byte store per thread and step.  Every run of source bytes (names, sequence / quality lines in
-// either direction, translated proteins) moves as a 16-byte window -- byte-reversed with four PRMT for --reverse,
-// mapped through the 256-byte table for --complement / case / dna2rna; only the literal bytes are placed one by one.
+// ---- the CTA's slice of the record table in shared memory + a chunk -> record map (k_emit, k_emit_contig)
+// s_off[i] = off[r0 + i] - o0 for the records r0 .. r0 + nr (clamped to int); s_map[c] = last record WITH output that
+// starts at or before 16-byte chunk c of the CTA (every such record marks the first chunk that starts inside it, a
+// prefix maximum fills the rest; chunks in front of the first mark get 0 and walk forward from there).
+static const u32 kSliceCap = 1024;
+__device__ __forceinline__ void cta_slice_map(const u64 *__restrict__ off, u32 r0, u32 nr, u64 o0, int *s_off, u32 *s_map,
+                                              u32 *s_wmax) {
+  constexpr u32 NCHUNK = 256 * kEmitChunks;
+  const u32 tid = threadIdx.x;
+  for (u32 i = tid; i <= nr; i += 256) {
+    const long long rel = (long long)off[r0 + i] - (long long)o0;
+    s_off[i] = rel > 0x7fffffffll ? 0x7fffffff : (rel < -0x7fffffffll ? -0x7fffffff : (int)rel);
+  }
+#pragma unroll
+  for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = 0;
+  __syncthreads();
+  for (u32 i = tid; i < nr; i += 256) {
+    const int b = s_off[i];
+    if (b > 0 && s_off[i + 1] > b) {
+      const u32 c = ((u32)b + 15u) >> 4;
+      if (c < NCHUNK) atomicMax(&s_map[c], i);
+    }
+  }
+  __syncthreads();
+  // inclusive prefix maximum: kEmitChunks consecutive entries per thread, warp scan, warp totals
+  u32 mx[kEmitChunks];
+  u32 run = 0;
+#pragma unroll
+  for (u32 q = 0; q < kEmitChunks; q++) {
+    const u32 x = s_map[kEmitChunks * tid + q];
+    run = x > run ? x : run;
+    mx[q] = run;
+  }
+  u32 inc = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+    if ((int)(tid & 31u) >= d && y > inc) inc = y;
+  }
+  if ((tid & 31u) == 31u) s_wmax[tid >> 5] = inc;
+  u32 before = __shfl_up_sync(0xffffffffu, inc, 1);
+  if ((tid & 31u) == 0u) before = 0;
+  __syncthreads();
+  for (u32 w = 0; w < (tid >> 5); w++) before = s_wmax[w] > before ? s_wmax[w] : before;
+#pragma unroll
+  for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = mx[q] > before ? mx[q] : before;
+  __syncthreads();
+}
+
+// 16 output bytes from position p of record ro on: every run of source bytes (names, sequence / quality lines in either
+// direction) moves as a 16-byte window -- byte-reversed with four PRMT for --reverse, mapped through the 256-byte table
+// for --complement / case / dna2rna; only the literal bytes are placed one by one.  next(r) steps to the following
+// record with output.
+template <class Next>
+__device__ __forceinline__ void emit_chunk_walk(const RecViews &v, const EmitCfg &c, RecOut ro, u32 p, long long rend, long long pos,
+                                                long long oend, const u8 *__restrict__ lut, u64 in_limit, u64 seq_limit,
+                                                u64 qual_limit, u32 w[4], Next next) {
+  const bool has_lut = lut != nullptr;
+  const long long o = pos;
+  while (pos < oend) {
+    if (pos >= rend) {
+      next(ro, rend, pos);
+      p = 0;
+    }
+    const Piece pc = piece_at(v, c, ro, p, has_lut);
+    u32 cnt = pc.len;
+    if (cnt > oend - pos) cnt = (u32)(oend - pos);
+    const u32 shift = (u32)(pos - o);
+    if (pc.kind == 0) {
+      w[shift >> 2] |= (u32)pc.lit << (8 * (shift & 3));
+    } else {
+      // Window of 16 source bytes laid out so that chunk byte shift+t holds the t-th byte of the run: forward runs
+      // start the window at src - shift; reversed runs end it at src + shift and are byte-reversed after the load.
+      const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
+      const bool fits = pc.rev ? (pc.src + shift >= 15) : (pc.src >= shift);
+      if (fits) {
+        u32 ww[4];
+        if (!pc.rev) {
+          window16(pc.base, pc.src - shift, limit, ww);
+        } else {
+          u32 t4[4];
+          window16(pc.base, pc.src + shift - 15, limit, t4);
+          ww[0] = __byte_perm(t4[3], 0, 0x0123);
+          ww[1] = __byte_perm(t4[2], 0, 0x0123);
+          ww[2] = __byte_perm(t4[1], 0, 0x0123);
+          ww[3] = __byte_perm(t4[0], 0, 0x0123);
+        }
+        if (pc.map) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const u32 x = ww[q];
+            ww[q] = (u32)lut[x & 0xffu] | ((u32)lut[(x >> 8) & 0xffu] << 8) | ((u32)lut[(x >> 16) & 0xffu] << 16) |
+                    ((u32)lut[x >> 24] << 24);
+          }
+        }
+        merge16(w, ww, shift, cnt);
+      } else {
+        for (u32 t = 0; t < cnt; t++) w[(shift + t) >> 2] |= (u32)rec_byte(v, c, ro, p + t, lut) << (8 * ((shift + t) & 3));
+      }
+    }
+    pos += cnt;
+    p += cnt;
+  }
+}
+
+// One aligned 16-byte store per thread and step.  The CTA's slice of the record table is staged in shared memory with a
+// chunk -> record map (no binary search per chunk).  A chunk that lies inside ONE run of source bytes (the middle of a
+// name, sequence or quality line: most of them) is one window and one store; the chunks that cross a piece or record
+// boundary -- one or two lanes of every warp, which would make the whole warp run the general walk -- go on a list and
+// are done side by side afterwards.  Slices of more than kSliceCap records (tiny records) take the walk for every chunk.
 __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
                                               u64 total, const u8 *__restrict__ lut, u64 in_limit, u64 seq_limit, u64 qual_limit) {
+  constexpr u32 NCHUNK = 256 * kEmitChunks;
   __shared__ u32 s_r[2];
-  const u64 o0 = (u64)blockIdx.x * blockDim.x * 16ull * kEmitChunks;
+  __shared__ int s_off[kSliceCap + 2];
+  __shared__ u32 s_map[NCHUNK];
+  __shared__ u32 s_wmax[8];
+  __shared__ unsigned short s_slow[NCHUNK];
+  __shared__ u32 s_nslow;
+  const u32 tid = threadIdx.x;
+  if (tid == 0) s_nslow = 0;
+  const u64 o0 = (u64)blockIdx.x * NCHUNK * 16ull;
   cta_record_range(off, v.n_rec, o0, total, s_r);
+  const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;
   const bool has_lut = lut != nullptr;
-  for (u32 ch = 0; ch < kEmitChunks; ch++) {
-    const u64 o = o0 + ((u64)ch * blockDim.x + threadIdx.x) * 16ull;
-    if (o >= total) return;
-    u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
-    RecOut ro = load_rec(v, c, r);
-    u64 rend = off[r + 1];
-    u32 p = (u32)(o - off[r]);
-    u32 w[4] = {0, 0, 0, 0};
-    u64 pos = o;
-    const u64 oend = o + 16 < total ? o + 16 : total;
-    while (pos < oend) {
-      if (pos >= rend) {
-        do {
-          r++;
-          rend = off[r + 1];
-        } while (pos >= rend);
-        ro = load_rec(v, c, r);
-        p = 0;
+  if (nr <= kSliceCap) {
+    cta_slice_map(off, r0, nr, o0, s_off, s_map, s_wmax);
+    auto locate = [&](u32 cidx, u32 &i, int &rbeg, int &rend) {
+      const int ro = (int)(cidx * 16u);
+      i = s_map[cidx];
+      rbeg = s_off[i];
+      rend = s_off[i + 1];
+      while (ro >= rend) {  // entry 0 of the map may be a record without output
+        i++;
+        rbeg = rend;
+        rend = s_off[i + 1];
       }
-      const Piece pc = piece_at(v, c, ro, p, has_lut);
-      u32 cnt = pc.len;
-      if (cnt > oend - pos) cnt = (u32)(oend - pos);
-      const u32 shift = (u32)(pos - o);
-      if (pc.kind == 0) {
-        w[shift >> 2] |= (u32)pc.lit << (8 * (shift & 3));
-      } else {
-        // Window of 16 source bytes laid out so that chunk byte shift+t holds the t-th byte of the run: forward runs
-        // start the window at src - shift; reversed runs end it at src + shift and are byte-reversed after the load.
-        const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
-        const bool fits = pc.rev ? (pc.src + shift >= 15) : (pc.src >= shift);
-        if (fits) {
-          u32 ww[4];
-          if (!pc.rev) {
-            window16(pc.base, pc.src - shift, limit, ww);
-          } else {
-            u32 t4[4];
-            window16(pc.base, pc.src + shift - 15, limit, t4);
-            ww[0] = __byte_perm(t4[3], 0, 0x0123);
-            ww[1] = __byte_perm(t4[2], 0, 0x0123);
-            ww[2] = __byte_perm(t4[1], 0, 0x0123);
-            ww[3] = __byte_perm(t4[0], 0, 0x0123);
-          }
-          if (pc.map) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const u32 x = ww[q];
-              ww[q] = (u32)lut[x & 0xffu] | ((u32)lut[(x >> 8) & 0xffu] << 8) | ((u32)lut[(x >> 16) & 0xffu] << 16) |
-                      ((u32)lut[x >> 24] << 24);
+    };
+#pragma unroll 1
+    for (u32 ch = 0; ch < kEmitChunks; ch++) {
+      const u32 cidx = ch * 256u + tid;
+      const u64 o = o0 + (u64)cidx * 16ull;
+      if (o >= total) break;
+      bool done = false;
+      if (o + 16 <= total) {
+        u32 i;
+        int rbeg, rend;
+        locate(cidx, i, rbeg, rend);
+        const int ro = (int)(cidx * 16u);
+        if (rend >= ro + 16) {
+          const RecOut rc = load_rec(v, c, r0 + i);
+          const Piece pc = piece_at(v, c, rc, (u32)(ro - rbeg), has_lut);
+          const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
+          if (pc.kind == 1 && pc.len >= 16u && (!pc.rev || pc.src >= 15u)) {  // the whole chunk is one run of source bytes
+            u32 w[4];
+            if (!pc.rev) {
+              window16(pc.base, pc.src, limit, w);
+            } else {
+              u32 t4[4];
+              window16(pc.base, pc.src - 15, limit, t4);
+              w[0] = __byte_perm(t4[3], 0, 0x0123);
+              w[1] = __byte_perm(t4[2], 0, 0x0123);
+              w[2] = __byte_perm(t4[1], 0, 0x0123);
+              w[3] = __byte_perm(t4[0], 0, 0x0123);
             }
+            if (pc.map) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                const u32 x = w[q];
+                w[q] = (u32)lut[x & 0xffu] | ((u32)lut[(x >> 8) & 0xffu] << 8) | ((u32)lut[(x >> 16) & 0xffu] << 16) |
+                       ((u32)lut[x >> 24] << 24);
+              }
+            }
+            *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+            done = true;
           }
-          merge16(w, ww, shift, cnt);
-        } else {
-          for (u32 t = 0; t < cnt; t++) w[(shift + t) >> 2] |= (u32)rec_byte(v, c, ro, p + t, lut) << (8 * ((shift + t) & 3));
         }
       }
-      pos += cnt;
-      p += cnt;
+      if (!done) s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)cidx;
     }
+    __syncthreads();
+    const u32 nslow = s_nslow;
+    for (u32 t = tid; t < nslow; t += 256) {
+      const u32 cidx = s_slow[t];
+      const u64 o = o0 + (u64)cidx * 16ull;
+      const u64 oend = o + 16 < total ? o + 16 : total;
+      u32 i;
+      int rbeg, rend;
+      locate(cidx, i, rbeg, rend);
+      u32 w[4] = {0, 0, 0, 0};
+      emit_chunk_walk(v, c, load_rec(v, c, r0 + i), (u32)((int)(cidx * 16u) - rbeg), (long long)rend, (long long)(cidx * 16u),
+                      (long long)(oend - o0), lut, in_limit, seq_limit, qual_limit, w, [&](RecOut &ro, long long &re, long long pos) {
+                        do {
+                          i++;
+                          re = s_off[i + 1];
+                        } while (pos >= re);
+                        ro = load_rec(v, c, r0 + i);
+                      });
+      *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return;
+  }
+  for (u32 ch = 0; ch < kEmitChunks; ch++) {
+    const u64 o = o0 + ((u64)ch * 256u + tid) * 16ull;
+    if (o >= total) return;
+    u32 r = search_in(off, s_r[0], s_r[1] + 1, o);
+    const u64 oend = o + 16 < total ? o + 16 : total;
+    u32 w[4] = {0, 0, 0, 0};
+    emit_chunk_walk(v, c, load_rec(v, c, r), (u32)(o - off[r]), (long long)off[r + 1], (long long)o, (long long)oend, lut, in_limit,
+                    seq_limit, qual_limit, w, [&](RecOut &ro, long long &re, long long pos) {
+                      do {
+                        r++;
+                        re = (long long)off[r + 1];
+                      } while (pos >= re);
+                      ro = load_rec(v, c, r);
+                    });
     *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
@@ -314,7 +463,7 @@ __global__ void k_contig_check(RecViews v, EmitCfg c, const u8 *__restrict__ kee
 // first chunk that starts inside it, a prefix maximum fills the rest), so that a chunk costs three shared-memory loads
 // instead of a binary search; a chunk that lies inside one record (94 % of them for 150 bp reads) is one unaligned
 // 16-byte window and one store.  Slices of more than kContigCap records (tiny records) read the global arrays.
-static const u32 kContigCap = 1024;
+static const u32 kContigCap = kSliceCap;
 __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__restrict__ off, u8 *__restrict__ out, u64 total,
                                                      u32 in_bytes, int stage) {
   constexpr u32 NCHUNK = 256 * kEmitChunks;  // 16-byte chunks per CTA
@@ -332,46 +481,8 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
   const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;  // records r0 .. r0 + nr - 1; entry nr = end of the last one
   const bool staged = stage && nr <= kContigCap;
   if (staged) {
-    for (u32 i = tid; i <= nr; i += 256) {
-      const long long rel = (long long)off[r0 + i] - (long long)o0;
-      s_off[i] = rel > 0x7fffffffll ? 0x7fffffff : (rel < -0x7fffffffll ? -0x7fffffff : (int)rel);
-      if (i < nr) s_src[i] = v.name_off[r0 + i] - 1u;
-    }
-#pragma unroll
-    for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = 0;
-    __syncthreads();
-    for (u32 i = tid; i < nr; i += 256) {
-      const int b = s_off[i];
-      if (b > 0 && s_off[i + 1] > b) {
-        const u32 c = ((u32)b + 15u) >> 4;
-        if (c < NCHUNK) atomicMax(&s_map[c], i);
-      }
-    }
-    __syncthreads();
-    {  // inclusive prefix maximum over the map: kEmitChunks consecutive entries per thread, warp scan, warp totals
-      u32 mx[kEmitChunks];
-      u32 run = 0;
-#pragma unroll
-      for (u32 q = 0; q < kEmitChunks; q++) {
-        const u32 x = s_map[kEmitChunks * tid + q];
-        run = x > run ? x : run;
-        mx[q] = run;
-      }
-      u32 inc = run;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 y = __shfl_up_sync(0xffffffffu, inc, d);
-        if ((int)(tid & 31u) >= d && y > inc) inc = y;
-      }
-      if ((tid & 31u) == 31u) s_wmax[tid >> 5] = inc;
-      u32 before = __shfl_up_sync(0xffffffffu, inc, 1);
-      if ((tid & 31u) == 0u) before = 0;
-      __syncthreads();
-      for (u32 w = 0; w < (tid >> 5); w++) before = s_wmax[w] > before ? s_wmax[w] : before;
-#pragma unroll
-      for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = mx[q] > before ? mx[q] : before;
-      __syncthreads();
-    }
+    for (u32 i = tid; i < nr; i += 256) s_src[i] = v.name_off[r0 + i] - 1u;
+    cta_slice_map(off, r0, nr, o0, s_off, s_map, s_wmax);
   }
   if (staged) {
     // phase 1: every chunk that lies inside one record issues its five word loads; nothing waits for them yet, so a
