@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
   __shared__ u32 s_wmax[8];
   __shared__ unsigned short s_slow[NCHUNK];
   __shared__ u32 s_nslow;
+  constexpr u32 kRecCap = 256;
+  __shared__ u32 s_rec[kRecCap][6];
   const u32 tid = threadIdx.x;
   if (tid == 0) s_nslow = 0;
   const u64 o0 = (u64)blockIdx.x * NCHUNK * 16ull;
@@ -344,6 +346,34 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
   const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;
   const bool has_lut = lut != nullptr;
   if (nr <= kSliceCap) {
+    // the views of the slice's records beside (up to kRecCap of them: reads and longer records; else from global memory)
+    const bool recs_staged = nr <= kRecCap;
+    if (recs_staged) {
+      for (u32 i = tid; i < nr; i += 256) {
+        const u32 r = r0 + i;
+        s_rec[i][0] = v.name_off[r];
+        s_rec[i][1] = v.name_len[r];
+        s_rec[i][2] = v.seq_off[r];
+        s_rec[i][3] = v.seq_len[r];
+        s_rec[i][4] = c.print_qual ? v.qual_off[r] : 0u;
+        s_rec[i][5] = c.print_qual ? v.qual_len[r] : 0u;
+      }
+    }
+    auto rec_of = [&](u32 i) {
+      if (!recs_staged) return load_rec(v, c, r0 + i);
+      RecOut o;
+      o.name_off = s_rec[i][0];
+      o.name_len = s_rec[i][1];
+      o.seq_off = s_rec[i][2];
+      o.seq_len = s_rec[i][3];
+      o.qual_off = s_rec[i][4];
+      o.qual_len = s_rec[i][5];
+      o.np = c.print_name ? (c.marker ? 1u : 0u) + o.name_len + 1u : 0u;
+      o.wl = wrap_len(o.seq_len, c.width);
+      o.ns = c.print_seq ? o.wl + 1u : 0u;
+      o.nq = c.print_qual ? (c.plus_line ? 2u : 0u) + o.qual_len + 1u : 0u;
+      return o;
+    };
     cta_slice_map(off, r0, nr, o0, s_off, s_map, s_wmax);
     auto locate = [&](u32 cidx, u32 &i, int &rbeg, int &rend) {
       const int ro = (int)(cidx * 16u);
@@ -368,7 +398,7 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
         locate(cidx, i, rbeg, rend);
         const int ro = (int)(cidx * 16u);
         if (rend >= ro + 16) {
-          const RecOut rc = load_rec(v, c, r0 + i);
+          const RecOut rc = rec_of(i);
           const Piece pc = piece_at(v, c, rc, (u32)(ro - rbeg), has_lut);
           const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
           if (pc.kind == 1 && pc.len >= 16u && (!pc.rev || pc.src >= 15u)) {  // the whole chunk is one run of source bytes
@@ -408,13 +438,13 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
       int rbeg, rend;
       locate(cidx, i, rbeg, rend);
       u32 w[4] = {0, 0, 0, 0};
-      emit_chunk_walk(v, c, load_rec(v, c, r0 + i), (u32)((int)(cidx * 16u) - rbeg), (long long)rend, (long long)(cidx * 16u),
+      emit_chunk_walk(v, c, rec_of(i), (u32)((int)(cidx * 16u) - rbeg), (long long)rend, (long long)(cidx * 16u),
                       (long long)(oend - o0), lut, in_limit, seq_limit, qual_limit, w, [&](RecOut &ro, long long &re, long long pos) {
                         do {
                           i++;
                           re = s_off[i + 1];
                         } while (pos >= re);
-                        ro = load_rec(v, c, r0 + i);
+                        ro = rec_of(i);
                       });
       *reinterpret_cast<uint4 *>(out + o) = make_uint4(w[0], w[1], w[2], w[3]);
     }
