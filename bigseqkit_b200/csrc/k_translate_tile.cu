@@ -110,8 +110,7 @@ __device__ __forceinline__ u8 tt_aa_careful(const TranslateTileArgs &a, const tt
 // amino acids j0 .. j0 + naa - 1 (naa <= 16) of the element from plain A/C/G/T bases read in place: v[] receives them
 // packed 4 per word.  false when the bases are not plain (span flags), the input is wrapped too narrowly or the 64-byte
 // load window leaves the buffer: the caller then takes the careful path.
-__device__ __forceinline__ bool tt_aa_fast(const TranslateTileArgs &a, const tt::El &E, u32 j0, u32 naa, const u8 *s_aaf,
-                                           const u8 *s_aar, u32 v[4]) {
+__device__ __forceinline__ bool tt_aa_fast(const TranslateTileArgs &a, const tt::El &E, u32 j0, u32 naa, const u8 *s_aa, u32 v[4]) {
   const u32 Wi = a.width_in;
   if ((Wi && Wi < 48u) || E.l >= (1u << 30)) return false;
   const u32 nb = 3u * naa, i0 = E.start + 3u * j0;
@@ -152,32 +151,36 @@ __device__ __forceinline__ bool tt_aa_fast(const TranslateTileArgs &a, const tt:
       R[q] = (S[q] & keep) | (__funnelshift_r(S[q], S[q + 1], 2u) & ~keep);
     }
   }
-  u32 aa[16];
-  if (E.f > 0) {
-#pragma unroll
-    for (int t = 0; t < 16; t++) {
-      const int bit = 6 * t;
-      const u32 idx = (bit + 6 <= 32 * (bit / 32 + 1) ? (R[bit / 32] >> (bit & 31)) : __funnelshift_r(R[bit / 32], R[bit / 32 + 1], bit & 31)) & 63u;
-      aa[t] = s_aaf[idx];
-      if (t == 0 && a.init_m && j0 == 0 && ((a.start_fwd >> idx) & 1ull)) aa[0] = 'M';
-    }
-  } else {
-    // codon t of the '-' strand = window positions nb-1-3t .. nb-3-3t read downwards: move the window up so that
-    // it ends at position 48, then codon t is the 6-bit group at bit 90 - 6t whatever naa is
+  // The '-' strand reads the window downwards: move it up so that it ends at position 48 and reverse the order of the
+  // 48 two-bit groups -- codon t then sits at bits 6t .. 6t+5 with its FIRST base lowest, as on the '+' strand, and both
+  // strands share the look-up loop (s_aa[64 ..] is the complement-strand table under that index order).
+  u32 toff = 0;
+  if (E.f < 0) {
     const u32 sh = 6u * (16u - naa);
+    u32 r0 = R[0], r1 = R[1], r2 = R[2];
     if (sh) {
       const u32 ws = sh >> 5, bs = sh & 31u;
-      const u32 r0 = R[0], r1 = R[1], r2 = R[2];
-      if (ws == 0) { R[2] = __funnelshift_l(r1, r2, bs); R[1] = __funnelshift_l(r0, r1, bs); R[0] = r0 << bs; }
-      else if (ws == 1) { R[2] = __funnelshift_l(r0, r1, bs); R[1] = r0 << bs; R[0] = 0; }
-      else { R[2] = r0 << bs; R[1] = 0; R[0] = 0; }
+      const u32 x0 = r0, x1 = r1, x2 = r2;
+      if (ws == 0) { r2 = __funnelshift_l(x1, x2, bs); r1 = __funnelshift_l(x0, x1, bs); r0 = x0 << bs; }
+      else if (ws == 1) { r2 = __funnelshift_l(x0, x1, bs); r1 = x0 << bs; r0 = 0; }
+      else { r2 = x0 << bs; r1 = 0; r0 = 0; }
     }
+    r0 = __brev(r0); r1 = __brev(r1); r2 = __brev(r2);  // bit reversal, then the two bits of every group back in order
+    R[0] = ((r2 >> 1) & 0x55555555u) | ((r2 & 0x55555555u) << 1);
+    R[1] = ((r1 >> 1) & 0x55555555u) | ((r1 & 0x55555555u) << 1);
+    R[2] = ((r0 >> 1) & 0x55555555u) | ((r0 & 0x55555555u) << 1);
+    toff = 64u;
+  }
+  u32 aa[16];
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-      const int bit = 90 - 6 * t;
-      const u32 idx = (bit + 6 <= 32 * (bit / 32 + 1) ? (R[bit / 32] >> (bit & 31)) : __funnelshift_r(R[bit / 32], R[bit / 32 + 1], bit & 31)) & 63u;
-      aa[t] = s_aar[idx];
-      if (t == 0 && a.init_m && j0 == 0 && ((a.start_rev >> idx) & 1ull)) aa[0] = 'M';
+  for (int t = 0; t < 16; t++) {
+    const int bit = 6 * t;
+    const u32 idx = (bit + 6 <= 32 * (bit / 32 + 1) ? (R[bit / 32] >> (bit & 31)) : __funnelshift_r(R[bit / 32], R[bit / 32 + 1], bit & 31)) & 63u;
+    aa[t] = s_aa[idx | toff];
+    if (t == 0 && a.init_m && j0 == 0) {
+      // start codons: bit per index of the 64-entry tables as the host built them (complement strand: third base lowest)
+      const u32 io = toff ? (((idx & 3u) << 4) | (idx & 0xcu) | (idx >> 4)) : idx;
+      if (((toff ? a.start_rev : a.start_fwd) >> io) & 1ull) aa[0] = 'M';
     }
   }
 #pragma unroll
@@ -187,7 +190,7 @@ __device__ __forceinline__ bool tt_aa_fast(const TranslateTileArgs &a, const tt:
 
 // the bytes of 16-byte window w of the tile that belong to the wrapped protein of element E -> s_out
 __device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::El &E, u32 w, u64 cta0, u8 *s_out, const u8 *s_fwd,
-                                         const u8 *s_rev, const u8 *s_lut, const u8 *s_aaf, const u8 *s_aar) {
+                                         const u8 *s_rev, const u8 *s_lut, const u8 *s_aa) {
   const u32 Wo = a.width_out;
   const u64 wa = cta0 + 16ull * w, pa = E.eo + E.H + 2u, pb = pa + E.wrapl;
   if (pa >= wa + 16u || pb <= wa) return;  // no protein byte of this element in the window
@@ -204,7 +207,7 @@ __device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::E
   }
   const u32 naa = (k1 - k0) - (nlpos < 16u ? 1u : 0u);
   u32 v[4];
-  if (simple && naa && E.wrapl < (1u << 30) && tt_aa_fast(a, E, j0, naa, s_aaf, s_aar, v)) {
+  if (simple && naa && E.wrapl < (1u << 30) && tt_aa_fast(a, E, j0, naa, s_aa, v)) {
     if (nlpos < 16u) {  // the output line ends inside the piece: shift the tail up by one byte, put the '\n' in
       const int cut = (int)(8u * (nlpos - k0));
       u32 up[4];
@@ -239,6 +242,36 @@ __device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::E
   }
 }
 
+// window w of the tile lies wholly inside the wrapped protein of E: 16 bytes from plain bases, at most one wrap newline.
+// false (nothing written) when the window needs the careful path -- the caller leaves it to tt_piece.
+__device__ __forceinline__ bool tt_full(const TranslateTileArgs &a, const tt::El &E, u32 w, u64 cta0, u8 *s_out, const u8 *s_aa) {
+  const u32 Wo = a.width_out;
+  if ((Wo && Wo < 16u) || E.wrapl >= (1u << 30)) return false;
+  const u32 q0 = (u32)(cta0 + 16ull * w - (E.eo + E.H + 2u));  // offset of the window in the wrapped protein
+  u32 j0 = q0, nlpos = 16;
+  if (Wo) {
+    const u32 line = tt_div(q0, a.magic_out1), col = q0 - line * (Wo + 1u);
+    j0 = line * Wo + col;
+    if (Wo - col < 16u) nlpos = Wo - col;
+  }
+  u32 v[4];
+  if (!tt_aa_fast(a, E, j0, nlpos < 16u ? 15u : 16u, s_aa, v)) return false;
+  if (nlpos < 16u) {  // the output line ends inside the window: shift the tail up by one byte, put the '\n' in
+    const int cut = (int)(8u * nlpos);
+    u32 up[4];
+    up[0] = v[0] << 8;
+#pragma unroll
+    for (int q = 1; q < 4; q++) up[q] = __funnelshift_l(v[q - 1], v[q], 8u);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const u32 keep = tt_lowmask(cut - 32 * q), nl = tt_lowmask(cut + 8 - 32 * q) & ~keep;
+      v[q] = (v[q] & keep) | (0x0a0a0a0au & nl) | (up[q] & ~(keep | nl));
+    }
+  }
+  *reinterpret_cast<uint4 *>(s_out + 16u * w) = make_uint4(v[0], v[1], v[2], v[3]);
+  return true;
+}
+
 // A CTA formats 4096 output bytes in shared memory and writes them with aligned 16-byte stores: warps copy the headers
 // of the elements that touch the tile, every thread fills the protein bytes of one 16-byte window for the element the
 // window starts in, and the few windows that reach into a further element's protein leave an item in a short list
@@ -249,7 +282,7 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
   __shared__ u8 s_fwd[256], s_rev[256];
   __align__(16) __shared__ u8 s_lut[4096];
   __align__(16) __shared__ u8 s_out[TILE];
-  __shared__ u8 s_aaf[64], s_aar[64];
+  __shared__ u8 s_aa[128];  // plain-codon tables: '+' strand, then the complement strand with the first base lowest
   __shared__ El s_el[ECAP];
   __shared__ u32 s_over[ICAP];
   __shared__ u32 s_cnt, s_n;
@@ -259,7 +292,7 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
     s_fwd[tid] = x == 16 ? 0x10 : (x == 0 ? 0x20 : x);  // IUPAC mask 1..15; gap 0x10; not a nucleotide 0x20
     s_rev[tid] = y == 16 ? 0x10 : (y == 0 ? 0x20 : y);
     reinterpret_cast<uint4 *>(s_lut)[tid] = reinterpret_cast<const uint4 *>(a.lut)[tid];
-    if (tid < 64) { s_aaf[tid] = a.aa_fwd[tid]; s_aar[tid] = a.aa_rev[tid]; }
+    if (tid < 64) { s_aa[tid] = a.aa_fwd[tid]; s_aa[64u + (((tid & 3u) << 4) | (tid & 0xcu) | (tid >> 4))] = a.aa_rev[tid]; }
     if (tid == 0) { s_n = 0; s_cnt = 0xffffffffu; }
   }
   const u32 n_el = a.n_rec * a.nf;
@@ -306,7 +339,15 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
       El E;
       if (lo < ECAP) E = s_el[lo];
       else tt_load_el(a, e_lo + lo, E);
-      tt_piece(a, E, tid, cta0, s_out, s_fwd, s_rev, s_lut, s_aaf, s_aar);
+      // a window inside one protein is done here; windows at the ends of a protein (one or two lanes of every warp) and
+      // the ones that need the careful path join the list, so that no warp runs the general piece code for one lane
+      const u64 pa = E.eo + E.H + 2u, pb = pa + E.wrapl;
+      bool done = pa >= wa + 16u || pb <= wa;  // no protein byte of the element in the window
+      if (!done && pa <= wa && wa + 16u <= pb) done = tt_full(a, E, tid, cta0, s_out, s_aa);
+      if (!done) {
+        const u32 slot = atomicAdd(&s_n, 1u);
+        if (slot < ICAP) s_over[slot] = (lo << 8) | tid;
+      }
       for (u32 k2 = lo + 1; k2 < cnt; k2++) {
         const u64 on = k2 < ECAP ? s_el[k2].eo : a.out_off[e_lo + k2];
         if (on >= wa + 16u) break;
@@ -316,13 +357,13 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
     }
   }
   __syncthreads();
-  const u32 n_over = s_n < ICAP ? s_n : ICAP;  // cannot overflow: one item per element that starts inside the tile
+  const u32 n_over = s_n < ICAP ? s_n : ICAP;  // cannot overflow: one item per window + one per element that starts inside the tile
   for (u32 it = tid; it < n_over; it += NT) {
     const u32 item = s_over[it], k2 = item >> 8;
     El E;
     if (k2 < ECAP) E = s_el[k2];
     else tt_load_el(a, e_lo + k2, E);
-    tt_piece(a, E, item & 0xffu, cta0, s_out, s_fwd, s_rev, s_lut, s_aaf, s_aar);
+    tt_piece(a, E, item & 0xffu, cta0, s_out, s_fwd, s_rev, s_lut, s_aa);
   }
   __syncthreads();
   const u64 o = cta0 + 16ull * tid;
