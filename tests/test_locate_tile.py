@@ -119,6 +119,15 @@ def test_edges(lib):
     _check(lib, b">pal\nACGTACGTACGT\n", {"Pattern": ["ACGT"]})            # palindrome: '+' and '-' needles share a code
 
 
+def test_large_panel_takes_general_path(lib):
+    """more than 2048 needle codes (patterns x strands) would overfill the fingerprint table of the tile kernel"""
+    rng = random.Random(21)
+    data = _fasta(rng, [6000, 300], 60)
+    pats = sorted(set(_panel(rng, data, 12, 1100, from_data=0.05)))
+    _check(lib, data, {"Pattern": pats}, expect_tile=len(pats) * 2 <= 2048)
+    _check(lib, data, {"Pattern": pats[:1000]}, expect_tile=True)
+
+
 def test_mixed_panel_takes_general_path(lib):
     rng = random.Random(12)
     data = _fasta(rng, [3000], 60)
