@@ -51,7 +51,7 @@ struct PinnedBuf {
     if (bytes <= cap) return;
     size_t want = bytes + bytes / 4 + 4096;
     void *q = nullptr;
-    BSK_CUDA(cudaHostAlloc(&q, want, cudaHostAllocDefault));
+    BSK_CUDA(cudaHostAlloc(&q, want, cudaHostAllocMapped | cudaHostAllocPortable));  // kernels may write it (prim::copy_small)
     if (p) {
       if (preserve && used) memcpy(q, p, used);
       cudaFreeHost(p);

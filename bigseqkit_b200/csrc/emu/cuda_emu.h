@@ -83,6 +83,7 @@ static inline int __syncthreads_count(int p) {
   return r;
 }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 
@@ -211,7 +212,7 @@ typedef void *cudaStream_t;
 typedef struct emuEvent { double t; } *cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 static inline const char *cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }

@@ -24,7 +24,7 @@ Engine::Engine(Op op, const Opts &o, int device) : op_(op), o_(o), device_(devic
   if (device_ >= 0) BSK_CUDA(cudaSetDevice(device_));
   BSK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   BSK_CUDA(cudaMalloc((void **)&d_status_, sizeof(DevStatus)));
-  BSK_CUDA(cudaHostAlloc((void **)&h_status_, sizeof(DevStatus), cudaHostAllocDefault));
+  BSK_CUDA(cudaHostAlloc((void **)&h_status_, sizeof(DevStatus), cudaHostAllocMapped | cudaHostAllocPortable));
   h_small_.reserve(16384);
   for (auto &e : ev_) BSK_CUDA(cudaEventCreate(&e));
   // constant tables: class[256] valid[256] lut[256] gap[256] aux[256] qpow[256 doubles]
@@ -88,15 +88,26 @@ int Engine::stage_device(const u8 *in, size_t n, void **d_ptr) {
   return BSK_OK;
 }
 
+// The status words travel by kernel, not by copy engine (prims.h: copy_small): the pipeline of bsk_run_buffer keeps both
+// engines busy with block-sized copies, and a small copy of this stream would wait behind them.
+static __global__ void k_status_reset(DevStatus *st) {
+  if (threadIdx.x == 0) {
+    DevStatus z;
+    memset(&z, 0, sizeof z);
+    z.err = kNoErr;
+    z.guess_mask = 0xffffffffu;
+    *st = z;
+  }
+}
 void Engine::reset_status() {
   memset(h_status_, 0, sizeof(DevStatus));
   h_status_->err = kNoErr;
   h_status_->guess_mask = 0xffffffffu;
-  BSK_CUDA(cudaMemcpyAsync(d_status_, h_status_, sizeof(DevStatus), cudaMemcpyHostToDevice, stream));
+  BSK_LAUNCH_FLAT(k_status_reset, 1, 32, 0, stream, d_status_);
 }
 
 void Engine::fetch_status() {
-  BSK_CUDA(cudaMemcpyAsync(h_status_, d_status_, sizeof(DevStatus), cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(h_status_, d_status_, (u32)sizeof(DevStatus), stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
 }
 
@@ -131,7 +142,7 @@ void Engine::set_views_default() {
 int Engine::prepare_block_tile(const u8 *d_in, u32 n) {
   if (n == 0 || !fused_ok_ || getenv("BSK_NO_TILE_INDEX")) return kFusedFallback;
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, d_in, 1, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, d_in, 1, stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
   if (hs[0] != '@') return kFusedFallback;
   if (!n_sm_) {
@@ -149,7 +160,7 @@ int Engine::prepare_block_tile(const u8 *d_in, u32 n) {
   launches_++;
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
   prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
-  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, tile_base + n_tiles, 8, stream);
   fetch_status();  // synchronises the stream
   if (h_status_->counters[0]) return kFusedFallback;
   u64 nrec;
@@ -212,9 +223,9 @@ int Engine::prepare_block(const u8 *d_in, u32 n) {
   launches_++;
   prim::excl_scan_u64(tile_cnt, tile_base, n_tiles + 1, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
-  BSK_CUDA(cudaMemcpyAsync(hs + 8, d_in, 1, cudaMemcpyDeviceToHost, stream));
-  BSK_CUDA(cudaMemcpyAsync(hs + 9, d_in + (n - 1), 1, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, tile_base + n_tiles, 8, stream);
+  prim::copy_small(hs + 8, d_in, 1, stream);
+  prim::copy_small(hs + 9, d_in + (n - 1), 1, stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
   u64 tot;
   memcpy(&tot, hs, 8);
@@ -256,14 +267,14 @@ int Engine::prepare_block(const u8 *d_in, u32 n) {
     prim::excl_scan_u32(ra_.seq_len, sa, R, b_tmp_, stream);
     prim::excl_scan_u32(ra_.qual_len, qa, R, b_tmp_, stream);
     u8 *h2 = h_small_.as<u8>();
-    BSK_CUDA(cudaMemcpyAsync(h2, sa + n_rec_, 4, cudaMemcpyDeviceToHost, stream));
-    BSK_CUDA(cudaMemcpyAsync(h2 + 4, qa + n_rec_, 4, cudaMemcpyDeviceToHost, stream));
+    prim::copy_small(h2, sa + n_rec_, 4, stream);
+    prim::copy_small(h2 + 4, qa + n_rec_, 4, stream);
     const bool try_uniform = !fastq_ && getenv("BSK_NO_UNIFORM_SQUEEZE") == nullptr;
     if (try_uniform) {  // FASTA wrapped at a fixed width (every writer's output): no per-line work needed
       BSK_CUDA(cudaMemsetAsync(&d_status_->counters[7], 0, 8, stream));
       k::lines_uniform(ix_, &d_status_->counters[7], stream);
       launches_++;
-      BSK_CUDA(cudaMemcpyAsync(h2 + 8, &d_status_->counters[7], 8, cudaMemcpyDeviceToHost, stream));
+      prim::copy_small(h2 + 8, &d_status_->counters[7], 8, stream);
     }
     BSK_CUDA(cudaStreamSynchronize(stream));
     u32 stot, qtot;
@@ -354,20 +365,20 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
   launches_++;
   prim::excl_scan_u32_to_u64(olen, ooff, R, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, ooff + n_rec_, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, ooff + n_rec_, 8, stream);
   u32 *d_nsel = &d_status_->n_sel;
   u64 *elem = nullptr;
   if (want_elem_off) {
     elem = b_elem_.get<u64>(R + 1);
     if (keep) {
       prim::select_flagged_u64(ooff, keep, elem, d_nsel, n_rec_, b_tmp_, stream);
-      BSK_CUDA(cudaMemcpyAsync(hs + 8, d_nsel, 4, cudaMemcpyDeviceToHost, stream));
+      prim::copy_small(hs + 8, d_nsel, 4, stream);
     }
   } else if (keep) {
     // still need the element count: count kept records through the same select on a scratch
     elem = b_elem_.get<u64>(R + 1);
     prim::select_flagged_u64(ooff, keep, elem, d_nsel, n_rec_, b_tmp_, stream);
-    BSK_CUDA(cudaMemcpyAsync(hs + 8, d_nsel, 4, cudaMemcpyDeviceToHost, stream));
+    prim::copy_small(hs + 8, d_nsel, 4, stream);
   }
   // records printed exactly as they stand in the input (rmdup, grep, filters on single-line records) are compacted
   // as byte ranges instead of being re-formatted byte by byte
@@ -378,7 +389,7 @@ int Engine::emit_records(const EmitCfg &cfg, const u8 *keep, const u8 *lut, Bloc
     BSK_CUDA(cudaMemsetAsync(&d_status_->counters[7], 0, 8, stream));
     k::contig_check(views_, cfg, keep, fastq_ ? 1 : 0, n_, &d_status_->counters[7], stream);
     launches_++;
-    BSK_CUDA(cudaMemcpyAsync(hs + 16, &d_status_->counters[7], 8, cudaMemcpyDeviceToHost, stream));
+    prim::copy_small(hs + 16, &d_status_->counters[7], 8, stream);
   }
   BSK_CUDA(cudaStreamSynchronize(stream));
   u64 total;

@@ -229,7 +229,7 @@ int Engine::op_duplicate(BlockOut &bo) {
   if (!n_rec_ || o_.Times == 0) return BSK_OK;
   if (o_.Times > 0xffffffffll) { err = "duplicate: times is too large"; return BSK_ERR_ARG; }
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, in_ + n_ - 1, 1, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, in_ + n_ - 1, 1, stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
   const int add_nl = hs[0] != '\n';
   const u64 total = (u64)o_.Times * ((u64)n_ + (add_nl ? 1u : 0u));
@@ -261,9 +261,9 @@ int Engine::op_range(BlockOut &bo) {
   if (b > (int64_t)n_rec_) b = n_rec_;
   if (b <= a) return BSK_OK;
   u32 *hs = h_small_.as<u32>();
-  BSK_CUDA(cudaMemcpyAsync(hs, ra_.head_off + a, 4, cudaMemcpyDeviceToHost, stream));
-  if (b < (int64_t)n_rec_) BSK_CUDA(cudaMemcpyAsync(hs + 1, ra_.head_off + b, 4, cudaMemcpyDeviceToHost, stream));
-  BSK_CUDA(cudaMemcpyAsync(hs + 2, in_ + n_ - 1, 1, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, ra_.head_off + a, 4, stream);
+  if (b < (int64_t)n_rec_) prim::copy_small(hs + 1, ra_.head_off + b, 4, stream);
+  prim::copy_small(hs + 2, in_ + n_ - 1, 1, stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
   const u32 s_a = hs[0] - 1u, s_b = b < (int64_t)n_rec_ ? hs[1] - 1u : n_;
   const bool add_nl = b == (int64_t)n_rec_ && *reinterpret_cast<const u8 *>(hs + 2) != '\n';

@@ -445,7 +445,7 @@ int Engine::run_matcher(int mode, u8 *flags, u64 &n_hits) {
   launches_++;
   prim::excl_scan_u32(tiles, item_off, R, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, item_off + n_rec_, 4, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, item_off + n_rec_, 4, stream);
   BSK_CUDA(cudaStreamSynchronize(stream));
   u32 n_items;
   memcpy(&n_items, hs, 4);
@@ -744,13 +744,13 @@ int Engine::locate_rows(BlockOut &bo, int64_t pid, u64 n_hits) {
   }
   prim::excl_scan_u32_to_u64(row_len, row_off, H, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, row_off + n_hits, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, row_off + n_hits, 8, stream);
   u64 n_rows = n_hits;
   u64 *elem = nullptr;
   if (keep) {
     elem = b_elem_.get<u64>(H + 2);
     prim::select_flagged_u64(row_off, keep, elem + 1, &d_status_->n_sel, n_hits, b_tmp_, stream);
-    BSK_CUDA(cudaMemcpyAsync(hs + 8, &d_status_->n_sel, 4, cudaMemcpyDeviceToHost, stream));
+    prim::copy_small(hs + 8, &d_status_->n_sel, 4, stream);
   }
   BSK_CUDA(cudaStreamSynchronize(stream));
   u64 rows_bytes;

@@ -490,7 +490,7 @@ int Engine::op_rmdup_tile(const u8 *d_in, u32 n, BlockOut &bo, bool prepare_only
   u64 *tile_base = b_tile_base_.get<u64>((size_t)n_tiles + 1);
   prim::excl_scan_u32_to_u64(tile_cnt, tile_base, (size_t)n_tiles + 1, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, tile_base + n_tiles, 8, stream);
   fetch_status();  // synchronises the stream
   if (h_status_->counters[0] || (o_.IDNCBI && subject == 2)) {
     alphabet_ = saved_alpha;

@@ -268,7 +268,7 @@ int Engine::op_seq_inplace(const u8 *d_in, u32 n, bool fastq, const EmitCfg &cfg
     launches_++;
   }
   u8 *hs = h_small_.as<u8>();
-  BSK_CUDA(cudaMemcpyAsync(hs, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, tile_base + n_tiles, 8, stream);
   fetch_status();  // synchronises the stream
   if (h_status_->counters[0]) {
     if (getenv("BSK_DEBUG")) {

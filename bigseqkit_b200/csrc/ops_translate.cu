@@ -424,7 +424,7 @@ int Engine::op_translate_tile(const u8 *d_in, u32 n, BlockOut &bo) {
   launches_++;
   prim::excl_scan_u32_to_u64(sizes, out_off, (size_t)n_el + 1, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>() + 8192;
-  BSK_CUDA(cudaMemcpyAsync(hs, out_off + n_el, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, out_off + n_el, 8, stream);
   // tables while the scan runs
   u8 *tab = h_small_.as<u8>();
   translate_host_tables(tab);
@@ -532,7 +532,7 @@ int Engine::op_translate(BlockOut &bo) {
   launches_++;
   prim::excl_scan_u32_to_u64(ppad, poff, (size_t)n_el + 1, b_tmp_, stream);
   u8 *hs = h_small_.as<u8>() + 8192;
-  BSK_CUDA(cudaMemcpyAsync(hs, poff + n_el, 8, cudaMemcpyDeviceToHost, stream));
+  prim::copy_small(hs, poff + n_el, 8, stream);
   fetch_status();  // also syncs the copy above; errors are judged after the codon pass (earliest record wins)
   int rc = BSK_OK;
   u64 ptotal;
@@ -560,7 +560,7 @@ int Engine::op_translate(BlockOut &bo) {
     u32 *ho = hl + n_el + 1;
     BSK_LAUNCH_FLAT(k_tr_hdr_len, (n_el + 1 + 255) / 256, 256, 0, stream, views_, c, ids + R, ids + 3 * R, hl);
     prim::excl_scan_u32(hl, ho, (size_t)n_el + 1, b_tmp_, stream);
-    BSK_CUDA(cudaMemcpyAsync(hs, ho + n_el, 4, cudaMemcpyDeviceToHost, stream));
+    prim::copy_small(hs, ho + n_el, 4, stream);
     BSK_CUDA(cudaStreamSynchronize(stream));
     u32 htotal;
     memcpy(&htotal, hs, 4);

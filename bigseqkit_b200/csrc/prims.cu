@@ -110,5 +110,14 @@ void sort_pairs_u64_u64(const uint64_t *kin, uint64_t *kout, const uint64_t *vin
                         int end_bit, DevBuf &, cudaStream_t) { sort_pairs_impl(kin, kout, vin, vout, n, begin_bit, end_bit); }
 #endif
 
+__global__ void k_copy_small(unsigned char *dst, const unsigned char *src, uint32_t n) {
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+void copy_small(void *dst, const void *src, uint32_t nbytes, cudaStream_t s) {
+  if (!nbytes) return;
+  BSK_LAUNCH_FLAT(k_copy_small, 1, nbytes < 128 ? 32 : 128, 0, s, static_cast<unsigned char *>(dst),
+                  static_cast<const unsigned char *>(src), nbytes);
+}
 }  // namespace prim
 }  // namespace bsk
