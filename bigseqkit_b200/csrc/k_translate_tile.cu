@@ -59,7 +59,7 @@ __device__ __forceinline__ u32 tt_lowmask(int nbits) {
 __device__ __forceinline__ u32 tt_div(u32 q, unsigned long long m) { return (u32)(((unsigned long long)q * m) >> 40); }
 
 namespace tt {
-constexpr u32 NT = 256, TILE = 4096, ICAP = 3072;
+constexpr u32 NT = 256, TILE = 4096, ICAP = 1664;  // ICAP: one item per window + one per element that starts in the tile (>= 3 bytes each)
 struct El {  // one (record, frame) element
   u64 eo;    // offset of its '>' in the output
   u32 r, H, l, s0, start, plen, wrapl, name_off;
@@ -81,16 +81,20 @@ __device__ __forceinline__ void tt_load_el(const TranslateTileArgs &a, u32 e, tt
 }
 
 // amino acid j of the element, byte by byte through the IUPAC tables (ambiguous / lower-case bases, gaps, errors)
-__device__ __forceinline__ u8 tt_aa_careful(const TranslateTileArgs &a, const tt::El &E, u32 j, const u8 *s_fwd, const u8 *s_rev,
-                                            const u8 *s_lut) {
+// (rare: the tables are read from global memory, L1 / L2 hits, instead of taking 4.5 KiB of every CTA's shared memory)
+__device__ __forceinline__ u32 tt_code(const u8 *tab, u8 b) {
+  const u32 x = tab[b];
+  return x == 16u ? 0x10u : (x == 0u ? 0x20u : x);  // IUPAC mask 1..15; gap 0x10; not a nucleotide 0x20
+}
+__device__ __forceinline__ u8 tt_aa_careful(const TranslateTileArgs &a, const tt::El &E, u32 j) {
   const u32 Wi = a.width_in, i = E.start + 3u * j, l = E.l;
   u32 b0, b1, b2;  // positions on the '+' strand
   if (E.f > 0) { b0 = i; b1 = i + 1u; b2 = i + 2u; }
   else { b0 = l - 1u - i; b1 = l - 2u - i; b2 = l - 3u - i; }
-  const u8 *tab = E.f > 0 ? s_fwd : s_rev;
-  const u32 c0 = tab[a.in[E.s0 + b0 + (Wi ? b0 / Wi : 0u)]];
-  const u32 c1 = tab[a.in[E.s0 + b1 + (Wi ? b1 / Wi : 0u)]];
-  const u32 c2 = tab[a.in[E.s0 + b2 + (Wi ? b2 / Wi : 0u)]];
+  const u8 *tab = E.f > 0 ? a.code_fwd : a.code_rev;
+  const u32 c0 = tt_code(tab, a.in[E.s0 + b0 + (Wi ? b0 / Wi : 0u)]);
+  const u32 c1 = tt_code(tab, a.in[E.s0 + b1 + (Wi ? b1 / Wi : 0u)]);
+  const u32 c2 = tt_code(tab, a.in[E.s0 + b2 + (Wi ? b2 / Wi : 0u)]);
   u8 c;
   bool init = false;
   if (c0 == 0x10 && c1 == 0x10 && c2 == 0x10) c = '-';
@@ -98,7 +102,7 @@ __device__ __forceinline__ u8 tt_aa_careful(const TranslateTileArgs &a, const tt
     c = 'X';
     if (!a.allow_unknown) atomicMin((unsigned long long *)&a.st->err, ((unsigned long long)E.r << 4) | EK_UNKNOWN_CODON);
   } else {
-    const u8 x = s_lut[(c0 << 8) | (c1 << 4) | c2];
+    const u8 x = a.lut[(c0 << 8) | (c1 << 4) | c2];
     c = x & 0x7f;
     init = (x & 0x80) != 0;
   }
@@ -189,8 +193,7 @@ __device__ __forceinline__ bool tt_aa_fast(const TranslateTileArgs &a, const tt:
 }
 
 // the bytes of 16-byte window w of the tile that belong to the wrapped protein of element E -> s_out
-__device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::El &E, u32 w, u64 cta0, u8 *s_out, const u8 *s_fwd,
-                                         const u8 *s_rev, const u8 *s_lut, const u8 *s_aa) {
+__device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::El &E, u32 w, u64 cta0, u8 *s_out, const u8 *s_aa) {
   const u32 Wo = a.width_out;
   const u64 wa = cta0 + 16ull * w, pa = E.eo + E.H + 2u, pb = pa + E.wrapl;
   if (pa >= wa + 16u || pb <= wa) return;  // no protein byte of this element in the window
@@ -237,7 +240,7 @@ __device__ __forceinline__ void tt_piece(const TranslateTileArgs &a, const tt::E
         is_nl = col == Wo;
         j = line * Wo + col;
       }
-      s_out[16u * w + k2] = is_nl ? (u8)'\n' : tt_aa_careful(a, E, j, s_fwd, s_rev, s_lut);
+      s_out[16u * w + k2] = is_nl ? (u8)'\n' : tt_aa_careful(a, E, j);
     }
   }
 }
@@ -276,11 +279,9 @@ __device__ __forceinline__ bool tt_full(const TranslateTileArgs &a, const tt::El
 // of the elements that touch the tile, every thread fills the protein bytes of one 16-byte window for the element the
 // window starts in, and the few windows that reach into a further element's protein leave an item in a short list
 // that is worked off round-robin afterwards (no divergent second pass of a whole warp).
-__global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) {
+__global__ void __launch_bounds__(tt::NT, 8) k_translate_tile(TranslateTileArgs a) {
   using namespace tt;
   constexpr u32 ECAP = 64;  // elements of the tile whose geometry is cached in shared memory
-  __shared__ u8 s_fwd[256], s_rev[256];
-  __align__(16) __shared__ u8 s_lut[4096];
   __align__(16) __shared__ u8 s_out[TILE];
   __shared__ u8 s_aa[128];  // plain-codon tables: '+' strand, then the complement strand with the first base lowest
   __shared__ El s_el[ECAP];
@@ -288,10 +289,6 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
   __shared__ u32 s_cnt, s_n;
   const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   {
-    const u8 x = a.code_fwd[tid], y = a.code_rev[tid];
-    s_fwd[tid] = x == 16 ? 0x10 : (x == 0 ? 0x20 : x);  // IUPAC mask 1..15; gap 0x10; not a nucleotide 0x20
-    s_rev[tid] = y == 16 ? 0x10 : (y == 0 ? 0x20 : y);
-    reinterpret_cast<uint4 *>(s_lut)[tid] = reinterpret_cast<const uint4 *>(a.lut)[tid];
     if (tid < 64) { s_aa[tid] = a.aa_fwd[tid]; s_aa[64u + (((tid & 3u) << 4) | (tid & 0xcu) | (tid >> 4))] = a.aa_rev[tid]; }
     if (tid == 0) { s_n = 0; s_cnt = 0xffffffffu; }
   }
@@ -363,7 +360,7 @@ __global__ void __launch_bounds__(tt::NT) k_translate_tile(TranslateTileArgs a) 
     El E;
     if (k2 < ECAP) E = s_el[k2];
     else tt_load_el(a, e_lo + k2, E);
-    tt_piece(a, E, item & 0xffu, cta0, s_out, s_fwd, s_rev, s_lut, s_aa);
+    tt_piece(a, E, item & 0xffu, cta0, s_out, s_aa);
   }
   __syncthreads();
   const u64 o = cta0 + 16ull * tid;
