@@ -238,9 +238,13 @@ __global__ void __launch_bounds__(st::G::NT, ALL ? 3 : 4) k_stats_tile(StatsTile
       // ---- work items: 4 lanes per line (a 150-byte line is 10-11 chunks: three steps), one aligned 16-byte chunk per lane and step.  The bytes of the chunk that
       // belong to the line are selected by a flag mask (bit 7 of byte i set iff lo <= i < hi) that is ANDed with the
       // flags of the byte tests, so no byte is masked itself.
+      // FASTQ items come in pairs (sequence line at the even index, quality line at the odd one): the sequence lines are
+      // done first, then the quality lines, so that the two kinds of byte tests never share a warp.
       const u32 n_item = sm.n_item;
       const u32 g = tid >> 2, gl = tid & 3u;
-      for (u32 ib = g; ib < n_item; ib += NT / 4) {
+      const u32 npass = fq ? 2u : 1u;
+      for (u32 pass = 0; pass < npass; pass++)
+      for (u32 ib = fq ? 2u * g + pass : g; ib < n_item; ib += fq ? NT / 2 : NT / 4) {
         const u32 e = sm.item[ib];
         const u32 p = e & 0x7fffu, L = (e >> 15) & 0x7fffu, kind = e >> 30;
         const u32 c1 = (p + L + 15u) & ~15u;
@@ -257,8 +261,9 @@ __global__ void __launch_bounds__(st::G::NT, ALL ? 3 : 4) k_stats_tile(StatsTile
             if (kind) {
               q20 += (u32)__popc(ge_flags4(w, c20) & m7);
               q30 += (u32)__popc(ge_flags4(w, c30) & m7);
-            } else if (!a.gap_below_40 || (((w | (w >> 1)) & 0x40404040u) != 0x40404040u)) {
-              // only words holding a byte below 0x40 can hold one of the (sub-'@') gap letters
+            } else if (!a.gap_below_40 || ((((w | (w >> 1)) & 0x40404040u) | ((m7 >> 1) ^ 0x40404040u)) != 0x40404040u)) {
+              // only words holding a byte below 0x40 INSIDE the line can hold one of the (sub-'@') gap letters; the
+              // bytes around the line (its '\n' is below 0x40) must not count, or some lane of every warp comes here
               u32 f = 0;
 #pragma unroll
               for (int j = 0; j < 4; j++)
