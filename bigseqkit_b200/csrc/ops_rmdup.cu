@@ -117,63 +117,19 @@ __device__ __forceinline__ bool subject_equal(const SubjectViews &sv, u32 a, u32
   return true;
 }
 
-// the same comparison by a whole warp (every lane calls it with the same a, b): lane j takes word j, j + 32, ...
-__device__ __forceinline__ bool subject_equal_warp(const SubjectViews &sv, u32 a, u32 b, int ignore_case) {
-  const u32 lane = threadIdx.x & 31u;
-  const u32 la = sv.len[a];
-  if (la != sv.len[b]) return false;
-  const u32 oa = sv.off[a], ob = sv.off[b];
-  const u8 *pa = sv.base + oa, *pb = sv.base + ob;
-  u32 diff = 0;
-  const u64 top = (u64)(oa > ob ? oa : ob) + la + 8u;
-  if (ignore_case) {
-    GetLower ga{pa}, gb{pb};
-    for (u32 i = lane; i < la; i += 32) diff |= (u32)(ga(i) != gb(i));
-  } else if (top > sv.limit || (((size_t)sv.base) & 3u)) {  // too close to the end of the buffer for word loads
-    for (u32 i = lane; i < la; i += 32) diff |= (u32)(pa[i] != pb[i]);
-  } else {
-    const u32 *wa = reinterpret_cast<const u32 *>(sv.base + (oa & ~3u)), *wb = reinterpret_cast<const u32 *>(sv.base + (ob & ~3u));
-    const u32 sa = (oa & 3u) * 8u, sb = (ob & 3u) * 8u;
-    const u32 nw = (la + 3u) >> 2;
-    for (u32 i = lane; i < nw; i += 32) {
-      u32 x = __funnelshift_r(wa[i], wa[i + 1], sa) ^ __funnelshift_r(wb[i], wb[i + 1], sb);
-      if (i + 1 == nw && (la & 3u)) x &= (1u << (8u * (la & 3u))) - 1u;
-      diff |= x;
-    }
-  }
-  return !__any_sync(0xffffffffu, diff != 0u);
-}
-
-// keep[r]: 1 first occurrence, 0 duplicate, 2 unresolved (64-bit key collision between different subjects).
-// A record whose key was seen earlier IN this block is compared byte for byte with that record -- by the whole warp, one
-// candidate after the other: a fifth of the lanes walking 150 bytes each while the rest of the warp waits cost 4x more.
+// keep[r]: 1 first occurrence, 0 duplicate, 2 unresolved (64-bit key collision between different subjects)
 __global__ void k_rmdup_resolve(SubjectViews sv, u32 n_rec, int ignore_case, const u64 *__restrict__ keys,
                                 const u64 *__restrict__ fps, u64 g_base, const u64 *__restrict__ hist_fp,
                                 const TableSlot *__restrict__ table, u64 cap, u8 *__restrict__ keep,
                                 u64 *__restrict__ first_out, DevStatus *st) {
-  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32: whole warps stay together
-  const u32 lane = threadIdx.x & 31u;
-  const bool valid = r < n_rec;
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rec) return;
   const u64 g = g_base + r;
-  u64 first = 0;
-  u8 k = 1;
-  bool cand = false;
-  if (valid) {
-    first = table_first(table, cap, keys[r]);
-    if (first == g) k = 1;
-    else if (first >= g_base) cand = true;
-    else k = (hist_fp[first] == fps[r]) ? 0 : 2;  // earlier block / other GPU: second 64-bit hash decides
-  }
-  u32 bal = __ballot_sync(0xffffffffu, cand);
-  while (bal) {
-    const u32 src = (u32)__ffs((int)bal) - 1u;
-    bal &= bal - 1u;
-    const u32 ra = __shfl_sync(0xffffffffu, r, (int)src);
-    const u32 rb = __shfl_sync(0xffffffffu, (u32)(first - g_base), (int)src);
-    const bool eq = subject_equal_warp(sv, ra, rb, ignore_case);
-    if (lane == src) k = eq ? 0 : 2;
-  }
-  if (!valid) return;
+  const u64 first = table_first(table, cap, keys[r]);
+  u8 k;
+  if (first == g) k = 1;
+  else if (first >= g_base) k = subject_equal(sv, r, (u32)(first - g_base), ignore_case) ? 0 : 2;
+  else k = (hist_fp[first] == fps[r]) ? 0 : 2;  // earlier block / other GPU: second 64-bit hash decides
   keep[r] = k;
   if (first_out) first_out[r] = first;  // ordinal of the group's first member (rmdup -D)
   if (k == 2) atomicAdd((unsigned long long *)&st->counters[4], 1ull);
@@ -314,7 +270,7 @@ int Engine::rmdup_resolve_block(BlockOut &bo) {
   if (n_rec_) {
     table_reserve(rm, g_base + n_rec_, stream, launches_);
     BSK_LAUNCH_FLAT(k_table_insert, (n_rec_ + 255) / 256, 256, 0, stream, keys, (u64)n_rec_, g_base, rm->table, rm->cap);
-    BSK_LAUNCH(k_rmdup_resolve, (n_rec_ + 255) / 256, 256, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps,
+    BSK_LAUNCH_FLAT(k_rmdup_resolve, (n_rec_ + 255) / 256, 256, 0, stream, sv, n_rec_, o_.IgnoreCase ? 1 : 0, keys, fps,
                     g_base, rm->hist_fp, rm->table, rm->cap, keep, first, d_status_);
     launches_ += 2;
     fetch_status();

@@ -1,20 +1,18 @@
 #!/bin/bash
 OUT=gpurun_out; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_parity_rmdup.py tests/test_parity_match.py tests/test_parity_seq.py -m gpu -x -q 2>&1 | tail -3
-( timeout 600 python bench.py --ops-only --ops rmdup --steps 10 --no-e2e --no-cpu-baseline 2> $OUT/r3e_bench.err ) > $OUT/r3e_bench.json
-tail -1 $OUT/r3e_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/r3e_launches_rmdup.csv \
-  python bench.py --ops-only --ops rmdup --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3e_ncu_rmdup.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_emit_contig -s 3 -c 1 -f -o $OUT/r3e_contig_prof \
-  python bench.py --ops-only --ops rmdup --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3e_ncu_contig.log 2>&1
+timeout 900 python -m pytest tests/test_parity_rmdup.py tests/test_exchange.py tests/test_formatter_seams.py -m gpu -x -q 2>&1 | tail -3
+( timeout 600 python bench.py --ops-only --ops rmdup --steps 10 --no-e2e --no-cpu-baseline 2> $OUT/r3l_bench.err ) > $OUT/r3l_bench.json
+tail -1 $OUT/r3l_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/r3l_launches_rmdup.csv \
+  python bench.py --ops-only --ops rmdup --steps 2 --warmup 3 --no-e2e --no-parity --no-cpu-baseline > $OUT/r3l_ncu_rmdup.log 2>&1
 python - <<'PY'
 import json,csv,collections
-for f in ('r3e_bench.json',):
+for f in ('r3l_bench.json',):
     try:
         d=json.loads(open('gpurun_out/'+f).read().strip().splitlines()[-1])
         for k,v in d['ops'].items(): print(f,k,'ms',round(v['ms_per_step'],4),'kernel_ms',round(v['roofline']['kernel_ms'],4),'frac',round(v['roofline']['frac'],4),v.get('parity',{}).get('match'))
     except Exception as e: print(f,'ERR',e)
-for f in ('r3e_launches_rmdup.csv',):
+for f in ('r3l_launches_rmdup.csv',):
     try:
         rows=[r for r in csv.reader(l for l in open('gpurun_out/'+f) if l.startswith('"'))]
         h=rows[0]; ki=h.index('Kernel Name'); vi=h.index('Metric Value')
