@@ -98,10 +98,11 @@ __device__ __forceinline__ u32 warp_search(const u64 *__restrict__ off, u32 n_re
 static const u32 kEmitChunks = 4;  // 16-byte chunks per thread: a CTA of 256 threads writes 16 KiB
 
 // record range [r0, r1] that covers the CTA's output bytes, found once per CTA
-__device__ __forceinline__ void cta_record_range(const u64 *__restrict__ off, u32 n_rec, u64 o0, u64 total, u32 *s_r) {
+__device__ __forceinline__ void cta_record_range(const u64 *__restrict__ off, u32 n_rec, u64 o0, u64 total, u32 *s_r,
+                                                 u64 cta_bytes = 256ull * 16ull * kEmitChunks) {
   const u32 warp = threadIdx.x >> 5;
   if (warp < 2) {
-    u64 o = warp == 0 ? o0 : o0 + (u64)blockDim.x * 16ull * kEmitChunks - 1;
+    u64 o = warp == 0 ? o0 : o0 + cta_bytes - 1;
     if (o >= total) o = total - 1;
     const u32 r = warp_search(off, n_rec, o);
     if ((threadIdx.x & 31) == 0) s_r[warp] = r;
@@ -223,16 +224,17 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
 // starts at or before 16-byte chunk c of the CTA (every such record marks the first chunk that starts inside it, a
 // prefix maximum fills the rest; chunks in front of the first mark get 0 and walk forward from there).
 static const u32 kSliceCap = 1024;
+template <u32 CH>
 __device__ __forceinline__ void cta_slice_map(const u64 *__restrict__ off, u32 r0, u32 nr, u64 o0, int *s_off, u32 *s_map,
                                               u32 *s_wmax) {
-  constexpr u32 NCHUNK = 256 * kEmitChunks;
+  constexpr u32 NCHUNK = 256 * CH;
   const u32 tid = threadIdx.x;
   for (u32 i = tid; i <= nr; i += 256) {
     const long long rel = (long long)off[r0 + i] - (long long)o0;
     s_off[i] = rel > 0x7fffffffll ? 0x7fffffff : (rel < -0x7fffffffll ? -0x7fffffff : (int)rel);
   }
 #pragma unroll
-  for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = 0;
+  for (u32 q = 0; q < CH; q++) s_map[CH * tid + q] = 0;
   __syncthreads();
   for (u32 i = tid; i < nr; i += 256) {
     const int b = s_off[i];
@@ -242,12 +244,12 @@ __device__ __forceinline__ void cta_slice_map(const u64 *__restrict__ off, u32 r
     }
   }
   __syncthreads();
-  // inclusive prefix maximum: kEmitChunks consecutive entries per thread, warp scan, warp totals
-  u32 mx[kEmitChunks];
+  // inclusive prefix maximum: CH consecutive entries per thread, warp scan, warp totals
+  u32 mx[CH];
   u32 run = 0;
 #pragma unroll
-  for (u32 q = 0; q < kEmitChunks; q++) {
-    const u32 x = s_map[kEmitChunks * tid + q];
+  for (u32 q = 0; q < CH; q++) {
+    const u32 x = s_map[CH * tid + q];
     run = x > run ? x : run;
     mx[q] = run;
   }
@@ -263,7 +265,7 @@ __device__ __forceinline__ void cta_slice_map(const u64 *__restrict__ off, u32 r
   __syncthreads();
   for (u32 w = 0; w < (tid >> 5); w++) before = s_wmax[w] > before ? s_wmax[w] : before;
 #pragma unroll
-  for (u32 q = 0; q < kEmitChunks; q++) s_map[kEmitChunks * tid + q] = mx[q] > before ? mx[q] : before;
+  for (u32 q = 0; q < CH; q++) s_map[CH * tid + q] = mx[q] > before ? mx[q] : before;
   __syncthreads();
 }
 
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *
       o.nq = c.print_qual ? (c.plus_line ? 2u : 0u) + o.qual_len + 1u : 0u;
       return o;
     };
-    cta_slice_map(off, r0, nr, o0, s_off, s_map, s_wmax);
+    cta_slice_map<kEmitChunks>(off, r0, nr, o0, s_off, s_map, s_wmax);
     auto locate = [&](u32 cidx, u32 &i, int &rbeg, int &rend) {
       const int ro = (int)(cidx * 16u);
       i = s_map[cidx];
@@ -494,9 +496,10 @@ __global__ void k_contig_check(RecViews v, EmitCfg c, const u8 *__restrict__ kee
 // instead of a binary search; a chunk that lies inside one record (94 % of them for 150 bp reads) is one unaligned
 // 16-byte window and one store.  Slices of more than kContigCap records (tiny records) read the global arrays.
 static const u32 kContigCap = kSliceCap;
+static const u32 kContigChunks = 8;  // 16-byte chunks per thread: a CTA writes 32 KiB (the prologue is paid once per CTA)
 __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__restrict__ off, u8 *__restrict__ out, u64 total,
                                                      u32 in_bytes, int stage) {
-  constexpr u32 NCHUNK = 256 * kEmitChunks;  // 16-byte chunks per CTA
+  constexpr u32 NCHUNK = 256 * kContigChunks;  // 16-byte chunks per CTA
   __shared__ u32 s_r[2];
   __shared__ int s_off[kContigCap + 2];   // off[r0 + i] - o0 (negative for a record that starts in front of the CTA)
   __shared__ u32 s_src[kContigCap + 2];   // first input byte of record r0 + i
@@ -507,21 +510,23 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
   const u32 tid = threadIdx.x;
   if (tid == 0) s_nslow = 0;
   const u64 o0 = (u64)blockIdx.x * NCHUNK * 16ull;
-  cta_record_range(off, v.n_rec, o0, total, s_r);
+  cta_record_range(off, v.n_rec, o0, total, s_r, (u64)NCHUNK * 16ull);
   const u32 r0 = s_r[0], nr = s_r[1] - s_r[0] + 1;  // records r0 .. r0 + nr - 1; entry nr = end of the last one
   const bool staged = stage && nr <= kContigCap;
   if (staged) {
     for (u32 i = tid; i < nr; i += 256) s_src[i] = v.name_off[r0 + i] - 1u;
-    cta_slice_map(off, r0, nr, o0, s_off, s_map, s_wmax);
+    cta_slice_map<kContigChunks>(off, r0, nr, o0, s_off, s_map, s_wmax);
   }
   if (staged) {
     // phase 1: every chunk that lies inside one record issues its five word loads; nothing waits for them yet, so a
     // thread has kEmitChunks x 20 bytes in flight (the kernel is bound by the bytes in flight per SM, not by issue)
-    u32 ld[kEmitChunks][5], sh[kEmitChunks];
-    bool fast[kEmitChunks];
+#pragma unroll 1
+    for (u32 half = 0; half < kContigChunks / 4; half++) {
+    u32 ld[4][5], sh[4];
+    bool fast[4];
 #pragma unroll
-    for (u32 ch = 0; ch < kEmitChunks; ch++) {
-      const u32 cidx = ch * 256u + tid;
+    for (u32 ch = 0; ch < 4; ch++) {
+      const u32 cidx = (half * 4u + ch) * 256u + tid;
       const u64 o = o0 + (u64)cidx * 16ull;
       fast[ch] = false;
       sh[ch] = 0;
@@ -549,8 +554,8 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
     // end) are put on a list and done afterwards by as many threads side by side -- inside this loop every warp would
     // run the general walk for its one lane.
 #pragma unroll
-    for (u32 ch = 0; ch < kEmitChunks; ch++) {
-      const u32 cidx = ch * 256u + tid;
+    for (u32 ch = 0; ch < 4; ch++) {
+      const u32 cidx = (half * 4u + ch) * 256u + tid;
       const u64 o = o0 + (u64)cidx * 16ull;
       if (fast[ch]) {
         u32 w[4];
@@ -560,6 +565,7 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
       } else if (o < total) {
         s_slow[atomicAdd(&s_nslow, 1u)] = (unsigned short)cidx;
       }
+    }
     }
     __syncthreads();
     const u32 nslow = s_nslow;
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(256) k_emit_contig(RecViews v, const u64 *__re
     }
     return;
   }
-  for (u32 ch = 0; ch < kEmitChunks; ch++) {
+  for (u32 ch = 0; ch < kContigChunks; ch++) {
     const u64 o = o0 + ((u64)ch * 256u + tid) * 16ull;
     if (o >= total) return;
     u32 w[4] = {0, 0, 0, 0};
@@ -635,7 +641,7 @@ void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes
 }
 void emit_contig(RecViews v, const u64 *out_off, u8 *out, u64 total, u32 in_bytes, cudaStream_t s) {
   if (!total) return;
-  const u64 per_cta = 256ull * 16 * kEmitChunks;
+  const u64 per_cta = 256ull * 16 * kContigChunks;
   static const int stage = [] { const char *e = getenv("BSK_CONTIG_STAGE"); return e ? atoi(e) : 1; }();  // A/B switch
   BSK_LAUNCH(k_emit_contig, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, out_off, out, total, in_bytes, stage);
 }
