@@ -330,7 +330,8 @@ __device__ __forceinline__ void emit_chunk_walk(const RecViews &v, const EmitCfg
 // name, sequence or quality line: most of them) is one window and one store; the chunks that cross a piece or record
 // boundary -- one or two lanes of every warp, which would make the whole warp run the general walk -- go on a list and
 // are done side by side afterwards.  Slices of more than kSliceCap records (tiny records) take the walk for every chunk.
-__global__ void __launch_bounds__(256) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
+template <int MB>
+__global__ void __launch_bounds__(256, MB) k_emit(RecViews v, EmitCfg c, const u64 *__restrict__ off, u8 *__restrict__ out,
                                               u64 total, const u8 *__restrict__ lut, u64 in_limit, u64 seq_limit, u64 qual_limit) {
   constexpr u32 NCHUNK = 256 * kEmitChunks;
   __shared__ u32 s_r[2];
@@ -632,8 +633,12 @@ void emit(RecViews v, EmitCfg c, const u64 *out_off, u8 *out, u64 total, const u
           u64 qual_limit, cudaStream_t s) {
   if (!total) return;
   const u64 per_cta = 256ull * 16 * kEmitChunks;
-  BSK_LAUNCH(k_emit, (u32)((total + per_cta - 1) / per_cta), 256, 0, s, v, c, out_off, out, total, lut, in_limit, seq_limit,
-             qual_limit);
+  // 6 CTAs / SM at 40 registers (124 B of spills) beat 4 at 62: subseq 2.48 -> 2.23 ms per GiB, seq --min-len 3.02 -> 2.64
+  // (5: 2.29, 8: 2.25; profiles/r2_experiments.txt).  BSK_EMIT_MB=4 keeps the unconstrained build for A/B runs.
+  static const int mb = [] { const char *e = getenv("BSK_EMIT_MB"); return e ? atoi(e) : 6; }();
+  const u32 grid = (u32)((total + per_cta - 1) / per_cta);
+  if (mb != 4) BSK_LAUNCH(k_emit<6>, grid, 256, 0, s, v, c, out_off, out, total, lut, in_limit, seq_limit, qual_limit);
+  else BSK_LAUNCH(k_emit<4>, grid, 256, 0, s, v, c, out_off, out, total, lut, in_limit, seq_limit, qual_limit);
 }
 void contig_check(RecViews v, EmitCfg c, const u8 *keep, int fastq, u32 in_bytes, u64 *n_bad, cudaStream_t s) {
   if (v.n_rec)
