@@ -24,6 +24,7 @@ namespace k {
 namespace ft {
 constexpr u32 NT = 256, SPAN = 96, REGION = NT * SPAN, LBL = 11, LB = LBL * SPAN, T = REGION - LB, NWARP = NT / 32;
 constexpr u32 NSTAGE = 2;
+constexpr u32 CTAS = 4;  // CTAs per SM (two 24 KiB stages each)
 constexpr u32 AHEAD = 16;  // bytes staged behind the tile: the byte after the tile's last newline
 struct Smem {
   u8 in[NSTAGE][REGION + AHEAD];
@@ -45,7 +46,7 @@ __device__ __forceinline__ u32 ft_not_acgt(u32 w, u32 nl) {
   return (expect ^ w) & ~((nl >> 7) * 0xffu);
 }
 
-__global__ void __launch_bounds__(ft::NT, 3) k_fasta_index_tile(FastaTileArgs a) {
+__global__ void __launch_bounds__(ft::NT, ft::CTAS) k_fasta_index_tile(FastaTileArgs a) {
   using namespace ft;
   BSK_DYN_SMEM(Smem, smp);
   Smem &sm = *smp;
@@ -261,7 +262,7 @@ void fasta_index_tile(FastaTileArgs a, int n_sm, cudaStream_t s) {
     attr_set[dev] = true;
   }
 #endif
-  u32 grid = (u32)n_sm * 3u;
+  u32 grid = (u32)n_sm * ft::CTAS;
   if (grid > a.n_tiles) grid = a.n_tiles;
   if (grid == 0) return;
   BSK_LAUNCH(k_fasta_index_tile, grid, ft::NT, smem, s, a);
