@@ -41,7 +41,7 @@ constexpr u32 T = REGION - LB;           // 23520 owned bytes per tile
 constexpr u32 WU = 16;                   // warm-up bytes in front of a lane's span (>= L - 1 symbols unless two newlines fall inside)
 constexpr u32 HDR_MAX = 960;             // longest header line accepted (must stay below LB - WU)
 constexpr u32 NWARP = NT / 32;
-constexpr u32 FBITS = 17;                // Bloom bitmap: 2^17 bits = 16 KiB, two probes per window
+constexpr u32 FBITS = 17;                // first-level bitmap: 2^17 bits = 16 KiB, one probe per window
 constexpr u32 FWORDS = (1u << FBITS) / 32;
 constexpr u32 PBITS = 12;                // fingerprint table: 2^12 x 16 bits = 8 KiB
 constexpr u32 QCAP = 256;                // candidates per tile parked for the confirmation pass
@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(lt::NT, lt::CTAS) k_locate_tile(LocateTileArgs
 
     // ---- 2-bit codes of the lane's span, one 16-byte chunk at a time (owned lanes only).  A chunk of 16 plain bases,
     // or of 15 and one newline, is packed with SWAR arithmetic (first base in the highest bits) and appended to the
-    // codes of the 16 bases before it; every window is then one funnel shift away.  Each window probes the Bloom
-    // bitmap; the few that pass both probes are parked in the queue and confirmed after the loop.  Any other chunk
+    // codes of the 16 bases before it; every window is then one funnel shift away.  Each window probes the
+    // bitmap; the few that also find their fingerprint are parked in the queue and confirmed after the loop.  Any other chunk
     // (invalid bases, header bytes, several newlines) goes byte by byte through the class table.
     // newline flags of the 16 bytes in front of the span = of the previous lane's last chunk
     const u32 prev_m2 = __shfl_up_sync(0xffffffffu, NCH == 3 ? (m[1] << 16) : m[2], 1);

@@ -125,9 +125,9 @@ struct LocateTileArgs {
   const u8 *in;
   u32 n, n_tiles;
   const u8 *lut;        // 256 byte classes (lt::C_*)
-  const u32 *filter;    // Bloom bitmap of the needle codes, locate_tile_filter_bits() bits (copied to shared memory)
+  const u32 *filter;    // first-level bitmap of the needle codes, locate_tile_filter_bits() bits, bit 31 - (i & 31) of word i >> 5
   const unsigned short *fptab;  // fingerprint table, 2^locate_tile_fp_bits() entries (copied to shared memory)
-  u32 kmul, kmul2;      // bit index i = (code * kmul_i) >> (32 - bits); kmul_i = odd << (32 - 2L)
+  u32 kmul, kmul2;      // bitmap index = (code * kmul) >> (32 - bits), fingerprint hash = code * kmul2; kmul_i = odd << (32 - 2L)
   u32 L, cmask;         // pattern length, mask of the 2L code bits
   u32 vmask, vbase;     // letters of the panel's case: (byte & vmask) must be one of vbase + {0, 2, 6, 0x13} in every byte
   const u32 *table;     // exact table: pairs {code, first needle + 1 (0 = empty)}, open addressing

@@ -506,7 +506,8 @@ int Engine::op_locate(BlockOut &bo, int64_t pid) {
   return locate_rows(bo, pid, n_hits);
 }
 
-// equal-length ACGT panel: 2-bit codes of the needles, Bloom bitmap for shared memory, exact table (host, once)
+// equal-length ACGT panel: 2-bit codes of the needles, first-level bitmap + fingerprint table for shared memory, exact
+// table (host, once)
 int Engine::build_kmer_tables() {
   PatternSet &ps = *pats_;
   if (ps.kmer_built) return BSK_OK;
