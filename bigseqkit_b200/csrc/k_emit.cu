@@ -158,54 +158,37 @@ __device__ __forceinline__ void merge16(u32 w[4], const u32 ww[4], u32 shift, u3
 // source buffer, or a run that needs the byte path (reversed and / or mapped sequence).
 struct Piece {
   u32 len;        // bytes in the piece from p on (>= 1)
-  int kind;       // 0 literal bytes (<= 3: lit32, first byte lowest), 1 run of source bytes
-  u32 lit32;
+  int kind;       // 0 literal, 1 run of source bytes
+  u8 lit;
   const u8 *base; // kind 1: source buffer and offset of the byte that comes out FIRST
   u64 src;
   bool rev;       // kind 1: the following output bytes come from DEcreasing source offsets
   bool map;       // kind 1: bytes go through the sequence byte map
 };
 
-// Adjacent pieces are merged where that saves iterations of the walk: marker + name + '\n' are ONE run when they stand in
-// the input like that (the usual case: same marker, the whole header line printed), and the "\n+\n" between sequence and
-// quality is one literal of three bytes.
-__device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, const RecOut &o, u32 p, bool has_lut, u64 in_limit) {
+__device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, const RecOut &o, u32 p, bool has_lut) {
   Piece pc;
   pc.base = nullptr;
   pc.src = 0;
   pc.rev = false;
   pc.map = false;
-  pc.lit32 = 0;
   if (p < o.np) {
-    const u32 m = c.marker ? 1u : 0u;  // positions: [0, m) marker, [m, m + name_len) name, np - 1 the newline
-    const bool lead = m && o.name_off >= 1u && v.in[o.name_off - 1u] == c.marker;
-    const u64 after = (u64)o.name_off + o.name_len;
-    const bool trail = after < in_limit && v.in[after] == '\n';
-    const u32 r0 = lead ? 0u : m, r1 = trail ? o.np : o.np - 1u;  // positions [r0, r1) are one run of input bytes
-    if (p >= r0 && p < r1) {
-      pc.kind = 1;
-      pc.len = r1 - p;
-      pc.base = v.in;
-      pc.src = (u64)o.name_off + p - m;  // p >= m, or p == 0 with the marker in front of the name
-      return pc;
+    u32 q = p;
+    if (c.marker) {
+      if (q == 0) { pc.kind = 0; pc.len = 1; pc.lit = c.marker; return pc; }
+      q--;
     }
-    pc.kind = 0;
-    pc.len = 1;
-    pc.lit32 = p < m ? (u32)c.marker : (u32)'\n';
+    if (q < o.name_len) { pc.kind = 1; pc.len = o.name_len - q; pc.base = v.in; pc.src = (u64)o.name_off + q; return pc; }
+    pc.kind = 0; pc.len = 1; pc.lit = '\n';
     return pc;
   }
   p -= o.np;
   if (p < o.ns) {
-    if (p == o.wl) {  // the newline behind the sequence, and the bare '+' line behind that
-      pc.kind = 0;
-      if (c.plus_line && c.print_qual) { pc.len = 3; pc.lit32 = 0x0a2b0au; }
-      else { pc.len = 1; pc.lit32 = '\n'; }
-      return pc;
-    }
+    if (p == o.wl) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
     u32 j = p, run = o.seq_len - p;
     if (c.width > 0) {
       const u32 line = p / (c.width + 1u), col = p - line * (c.width + 1u);
-      if (col == c.width) { pc.kind = 0; pc.len = 1; pc.lit32 = '\n'; return pc; }
+      if (col == c.width) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
       j = line * c.width + col;
       run = c.width - col;
       if (run > o.seq_len - j) run = o.seq_len - j;
@@ -220,8 +203,8 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
   }
   p -= o.ns;
   if (c.plus_line) {
-    if (p == 0) { pc.kind = 0; pc.len = 2; pc.lit32 = 0x0a2bu; return pc; }
-    if (p == 1) { pc.kind = 0; pc.len = 1; pc.lit32 = '\n'; return pc; }
+    if (p == 0) { pc.kind = 0; pc.len = 1; pc.lit = '+'; return pc; }
+    if (p == 1) { pc.kind = 0; pc.len = 1; pc.lit = '\n'; return pc; }
     p -= 2;
   }
   if (p < o.qual_len) {
@@ -232,7 +215,7 @@ __device__ __forceinline__ Piece piece_at(const RecViews &v, const EmitCfg &c, c
     pc.src = c.reverse ? (u64)o.qual_off + (o.qual_len - 1u - p) : (u64)o.qual_off + p;
     return pc;
   }
-  pc.kind = 0; pc.len = 1; pc.lit32 = '\n';
+  pc.kind = 0; pc.len = 1; pc.lit = '\n';
   return pc;
 }
 
@@ -301,15 +284,12 @@ __device__ __forceinline__ void emit_chunk_walk(const RecViews &v, const EmitCfg
       next(ro, rend, pos);
       p = 0;
     }
-    const Piece pc = piece_at(v, c, ro, p, has_lut, in_limit);
+    const Piece pc = piece_at(v, c, ro, p, has_lut);
     u32 cnt = pc.len;
     if (cnt > oend - pos) cnt = (u32)(oend - pos);
     const u32 shift = (u32)(pos - o);
     if (pc.kind == 0) {
-      const u32 lit = cnt >= 4u ? pc.lit32 : (pc.lit32 & ((1u << (8u * cnt)) - 1u));  // the bytes that fit the chunk
-      const u32 b = 8u * (shift & 3u);
-      w[shift >> 2] |= lit << b;
-      if (b && shift < 12u) w[(shift >> 2) + 1u] |= lit >> (32u - b);
+      w[shift >> 2] |= (u32)pc.lit << (8 * (shift & 3));
     } else {
       // Window of 16 source bytes laid out so that chunk byte shift+t holds the t-th byte of the run: forward runs
       // start the window at src - shift; reversed runs end it at src + shift and are byte-reversed after the load.
@@ -422,7 +402,7 @@ __global__ void __launch_bounds__(256, MB) k_emit(RecViews v, EmitCfg c, const u
         const int ro = (int)(cidx * 16u);
         if (rend >= ro + 16) {
           const RecOut rc = rec_of(i);
-          const Piece pc = piece_at(v, c, rc, (u32)(ro - rbeg), has_lut, in_limit);
+          const Piece pc = piece_at(v, c, rc, (u32)(ro - rbeg), has_lut);
           const u64 limit = pc.base == v.in ? in_limit : (pc.base == v.seqb ? seq_limit : qual_limit);
           if (pc.kind == 1 && pc.len >= 16u && (!pc.rev || pc.src >= 15u)) {  // the whole chunk is one run of source bytes
             u32 w[4];
